@@ -1,0 +1,407 @@
+// Kernel (2): conditional accumulation.  Bins every cell of a slice against the
+// slice's ascending fp64 edges (an exact np.digitize: arithmetic guess, then a
+// fix-up against the true edge values held in shared memory), accumulates K
+// weighted sums per bin in fp64 in warp-private shared-memory histograms, and a
+// second small kernel reduces the per-CTA partials in a fixed order and runs a
+// block-wide scan over bins.  Replaces xhistogram + cumsum
+// (xcontour/core.py:412-460, 1202-1325) and, with closed_right / SUFFIX, the 4-D
+// broadcast of core.py:363-409.
+//
+// Why warp-private, non-atomic histograms: sm_100a has no native shared-memory
+// fp64 (or 64-bit integer) add -- atomicAdd(double*) on shared memory compiles
+// to an ATOMS.CAST.SPIN loop -- so each warp owns a copy and resolves the lanes
+// that hit the same bin itself: every pending lane writes its lane id into a
+// byte tag for its bin, the lane that reads its own id back owns the bin for
+// this round and does a plain 128-bit read-modify-write, the rest retry.
+#include "common.cuh"
+#include "internal.h"
+#include <math_constants.h>
+
+namespace xc {
+
+constexpr int HIST_MAX_WARPS = 16;
+
+struct HistParams {
+    const void* q; long P; long per; long s0;
+    const double* edges; long edges_stride; int N; int closed_right;
+    const void* dA; int dA_f32; int acc_area;
+    const void* integ[XC_MAX_INTEGRANDS]; int integ_f32[XC_MAX_INTEGRANDS]; int n_int;
+    const uint8_t* q_mask;
+    double* part;            // [S][C][K][N]
+    int32_t* bin_idx;        // [S][P] or null
+    int ncopy;
+};
+
+struct EdgeGuess { double base, inv; int off; int uniform; };
+
+// Exact digitize against ascending e[0..N]; -1 when the cell is discarded.
+__device__ __forceinline__ int find_bin(double v, const double* e, int N,
+                                        const EdgeGuess& g, int closed_right)
+{
+    if (closed_right) { if (!(v > e[0]) || !(v <= e[N])) return -1; }
+    else              { if (!(v >= e[0]) || !(v < e[N])) return -1; }
+    int p;
+    if (g.uniform) {
+        double t = (v - g.base) * g.inv;
+        p = g.off + (int)fmin(fmax(t, -1.0), (double)N);
+        p = min(max(p, 0), N - 1);
+        if (closed_right) { while (v <= e[p]) --p; while (v > e[p + 1]) ++p; }
+        else              { while (v <  e[p]) --p; while (v >= e[p + 1]) ++p; }
+    } else {
+        int lo = 0, hi = N;            // first index with e[idx] > v  (or >= v)
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            bool right = closed_right ? (e[mid] < v) : (e[mid] <= v);
+            if (right) lo = mid + 1; else hi = mid;
+        }
+        p = lo - 1;
+    }
+    return p;
+}
+
+template <int K>
+__device__ __forceinline__ void rmw_add(double* h, const double (&w)[K])
+{
+    if (K == 2) {
+        double2 t = *reinterpret_cast<double2*>(h);
+        t.x += w[0]; t.y += w[1];
+        *reinterpret_cast<double2*>(h) = t;
+    } else if (K == 4) {
+        double2 a = reinterpret_cast<double2*>(h)[0], b = reinterpret_cast<double2*>(h)[1];
+        a.x += w[0]; a.y += w[1]; b.x += w[2]; b.y += w[3];
+        reinterpret_cast<double2*>(h)[0] = a; reinterpret_cast<double2*>(h)[1] = b;
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) h[k] += w[k];
+    }
+}
+
+// Warp-collective scatter-add into a warp-private histogram (all 32 lanes must
+// call).  Lanes with the same bin are serialised by the tag protocol.
+template <int K>
+__device__ __forceinline__ void scatter_private(double* H, uint8_t* tag, int bin,
+                                                const double (&w)[K], bool active, int lane)
+{
+    unsigned pending = __ballot_sync(XC_FULL, active);
+    while (pending) {
+        if (active) tag[bin] = (uint8_t)lane;
+        __syncwarp();
+        if (active && tag[bin] == (uint8_t)lane) {
+            rmw_add<K>(H + (size_t)bin * K, w);
+            active = false;
+        }
+        __syncwarp();
+        pending = __ballot_sync(XC_FULL, active);
+    }
+}
+
+template <int K>
+__device__ __forceinline__ void scatter_atomic(double* H, int bin, const double (&w)[K], bool active)
+{
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) atomicAdd(H + (size_t)bin * K + k, w[k]);
+    }
+}
+
+// grid = (C, nslices).  PRIVATE: one histogram copy per warp, no atomics.
+template <typename QT, int K, bool PRIVATE>
+__global__ void __launch_bounds__(HIST_MAX_WARPS * 32)
+k_hist(const HistParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int N = p.N;
+    double* e = reinterpret_cast<double*>(smem);
+    const int eN = (N + 2) & ~1;
+    double* H = e + eN;
+    uint8_t* tags = reinterpret_cast<uint8_t*>(H + (size_t)p.ncopy * N * K);
+    const int tagN = (N + 15) & ~15;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const long s = p.s0 + blockIdx.y;
+    const int  c = blockIdx.x, C = gridDim.x;
+
+    const double* eg = p.edges + s * p.edges_stride;
+    for (int k = tid; k <= N; k += blockDim.x) e[k] = eg[k];
+    for (int i = tid; i < p.ncopy * N * K; i += blockDim.x) H[i] = 0.0;
+    __syncthreads();
+
+    EdgeGuess g;
+    {
+        int a = isinf(e[0]) ? 1 : 0, b = isinf(e[N]) ? N - 1 : N;
+        double span = e[b] - e[a];
+        g.base = e[a]; g.off = a;
+        g.inv = (b > a && span > 0.0) ? (double)(b - a) / span : 0.0;
+        int bad = (g.inv == 0.0) || !isfinite(g.inv);
+        double h = (b > a) ? span / (double)(b - a) : 0.0;
+        for (int k = a + tid; k <= b; k += blockDim.x)
+            if (fabs(e[k] - (g.base + (double)(k - a) * h)) > h) bad = 1;
+        g.uniform = !__syncthreads_or(bad);
+    }
+
+    const QT* qs = reinterpret_cast<const QT*>(p.q) + s * p.P;
+    const long beg = (long)c * p.per;
+    const long end = beg + p.per < p.P ? beg + p.per : p.P;
+    double*  Hw   = H + (size_t)(warp % p.ncopy) * N * K;
+    uint8_t* tagw = tags + (size_t)warp * tagN;
+    const bool vec_ok = ((p.P & 3) == 0) && ((((uintptr_t)p.q) & 15) == 0);
+
+    for (long base = beg + (long)warp * 128; base < end; base += (long)nwarps * 128) {
+        const long i0 = base + lane * 4;
+        QT qv[4];
+        if (vec_ok && i0 + 3 < end) {
+            if (sizeof(QT) == 4) {
+                float4 t = __ldg(reinterpret_cast<const float4*>(qs + i0));
+                qv[0] = t.x; qv[1] = t.y; qv[2] = t.z; qv[3] = t.w;
+            } else {
+                double2 a = __ldg(reinterpret_cast<const double2*>(qs + i0));
+                double2 b = __ldg(reinterpret_cast<const double2*>(qs + i0) + 1);
+                qv[0] = a.x; qv[1] = a.y; qv[2] = b.x; qv[3] = b.y;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) qv[u] = (i0 + u < end) ? __ldg(qs + i0 + u) : (QT)CUDART_NAN;
+        }
+        int bins[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long i = i0 + u;
+            bool ok = i < end;
+            if (ok && p.q_mask) ok = p.q_mask[i] != 0;
+            bins[u] = ok ? find_bin((double)qv[u], e, N, g, p.closed_right) : -1;
+        }
+        if (p.bin_idx) {
+            int32_t* bo = p.bin_idx + s * p.P;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (i0 + u < end) bo[i0 + u] = bins[u];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long i = i0 + u;
+            const bool act = bins[u] >= 0;
+            double w[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) w[k] = 0.0;
+            if (act) {
+                int k = 0;
+                float  af = 0.f; double ad = 0.0;
+                if (p.dA_f32) { af = __ldg(reinterpret_cast<const float*>(p.dA) + i); ad = (double)af; }
+                else          { ad = __ldg(reinterpret_cast<const double*>(p.dA) + i); }
+                if (p.acc_area) { w[k++] = isnan(ad) ? 0.0 : ad; }
+#pragma unroll
+                for (int n = 0; n < XC_MAX_INTEGRANDS; ++n) {
+                    if (n < p.n_int && k < K) {
+                        double pr;
+                        if (p.integ_f32[n]) {
+                            float gf = __ldg(reinterpret_cast<const float*>(p.integ[n]) + s * p.P + i);
+                            // product rounded in the common dtype (core.py:444)
+                            pr = p.dA_f32 ? (double)__fmul_rn(gf, af) : __dmul_rn((double)gf, ad);
+                        } else {
+                            double gd = __ldg(reinterpret_cast<const double*>(p.integ[n]) + s * p.P + i);
+                            pr = __dmul_rn(gd, ad);
+                        }
+                        w[k++] = isnan(pr) ? 0.0 : pr;             // fillna(0), core.py:449
+                    }
+                }
+            }
+            if (PRIVATE) scatter_private<K>(Hw, tagw, bins[u], w, act, lane);
+            else         scatter_atomic<K>(Hw, bins[u], w, act);
+        }
+    }
+    __syncthreads();
+    double* out = p.part + ((size_t)(blockIdx.y + p.s0) * C + c) * K * N;
+    for (int idx = tid; idx < K * N; idx += blockDim.x) {
+        const int k = idx / N, n = idx - k * N;
+        double acc = 0.0;
+        for (int cp = 0; cp < p.ncopy; ++cp) acc += H[((size_t)cp * N + n) * K + k];
+        out[idx] = acc;
+    }
+}
+
+// grid = (S, K).  Fixed-order reduction of the C partials, then a block scan.
+__global__ void __launch_bounds__(256)
+k_reduce_scan(const double* __restrict__ part, int C, int K, int N, int scan_mode,
+              const int32_t* __restrict__ decreasing,
+              double* __restrict__ pdf, const ScanOut so)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    double* pd = reinterpret_cast<double*>(smem);       // N values, scan order
+    __shared__ double wtot[8];
+    __shared__ double total_s;
+    const long s = blockIdx.x; const int k = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool rev = decreasing && decreasing[s] != 0;
+    const bool suffix = scan_mode == XC_SCAN_SUFFIX;
+
+    for (int n = tid; n < N; n += blockDim.x) {
+        double acc = 0.0;
+        for (int c = 0; c < C; ++c) acc += part[(((size_t)s * C + c) * K + k) * N + n];
+        pd[suffix ? N - 1 - n : n] = acc;
+        if (pdf) pdf[((size_t)s * K + k) * N + (rev ? N - 1 - n : n)] = acc;
+    }
+    __syncthreads();
+    const int L = (N + blockDim.x - 1) / blockDim.x;
+    const int r0 = tid * L, r1 = min(N, r0 + L);
+    double loc = 0.0;
+    for (int r = r0; r < r1; ++r) loc += pd[r];
+    // exclusive scan of the 256 thread totals
+    double inc = loc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double t = __shfl_up_sync(XC_FULL, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wtot[warp] = inc;
+    __syncthreads();
+    double carry = 0.0;
+    for (int w = 0; w < warp; ++w) carry += wtot[w];
+    double run = carry + (inc - loc);
+    for (int r = r0; r < r1; ++r) { run += pd[r]; pd[r] = run; }
+    __syncthreads();
+    if (tid == 0) total_s = pd[N - 1];
+    __syncthreads();
+    const double total = total_s;
+    for (int r = tid; r < N; r += blockDim.x) {
+        const int n = suffix ? N - 1 - r : r;          // bin position (ascending edges)
+        double v = pd[r];
+        if (scan_mode == XC_SCAN_TOTAL_MINUS) v = total - v;
+        so.p[k][(size_t)s * so.stride + (rev ? N - 1 - n : n)] = v;
+    }
+}
+
+struct HistPlan { int C; int warps; int ncopy; bool priv; size_t smem; };
+
+static HistPlan plan_hist(long S, long P, int N, int K)
+{
+    HistPlan pl;
+    const size_t budget = 200 * 1024;
+    const size_t e_bytes = (size_t)((N + 2) & ~1) * 8;
+    const size_t copy_bytes = (size_t)N * K * 8, tag_bytes = (size_t)((N + 15) & ~15);
+    long fit = (long)((budget - e_bytes) / (copy_bytes + tag_bytes));
+    // two resident CTAs per SM when 16 private copies fit in half the budget
+    long fit_half = (long)((budget / 2 - e_bytes) / (copy_bytes + tag_bytes));
+    if (fit_half >= HIST_MAX_WARPS)      { pl.priv = true;  pl.warps = HIST_MAX_WARPS; pl.ncopy = pl.warps; }
+    else if (fit >= 8)                   { pl.priv = true;  pl.warps = (int)(fit > HIST_MAX_WARPS ? HIST_MAX_WARPS : fit); pl.ncopy = pl.warps; }
+    else {
+        pl.priv = false; pl.warps = HIST_MAX_WARPS;
+        long nc = (long)((budget - e_bytes) / copy_bytes);
+        pl.ncopy = (int)(nc > 8 ? 8 : nc);
+    }
+    pl.smem = e_bytes + (size_t)(pl.ncopy > 0 ? pl.ncopy : 0) * copy_bytes +
+              (pl.priv ? (size_t)pl.warps * tag_bytes : 0);
+    long want = (long)sm_count() * 4;
+    long C = (want + S - 1) / S;
+    long maxC = (P + 16383) / 16384;
+    if (C > maxC) C = maxC;
+    if (C < 1) C = 1;
+    pl.C = (int)C;
+    return pl;
+}
+
+template <typename QT, int K>
+static int launch_hist(const HistParams& hp, const HistPlan& pl, long ns, cudaStream_t st)
+{
+    dim3 grid((unsigned)pl.C, (unsigned)ns);
+    if (pl.priv) {
+        XC_CUDA_OK(cudaFuncSetAttribute(k_hist<QT, K, true>,
+                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        k_hist<QT, K, true><<<grid, pl.warps * 32, pl.smem, st>>>(hp);
+    } else {
+        XC_CUDA_OK(cudaFuncSetAttribute(k_hist<QT, K, false>,
+                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        k_hist<QT, K, false><<<grid, pl.warps * 32, pl.smem, st>>>(hp);
+    }
+    XC_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace xc
+
+using namespace xc;
+
+extern "C" size_t xc_bin_accumulate_workspace_bytes(long S, long P, int N, int K)
+{
+    if (S <= 0 || P <= 0 || N <= 0 || K <= 0) return 0;
+    HistPlan pl = plan_hist(S, P, N, K);
+    return 256 + (size_t)S * pl.C * K * N * sizeof(double);
+}
+
+extern "C" int xc_bin_accumulate(const void* q, int q_dtype, long S, long P,
+                                 const double* edges, long edges_stride, int N,
+                                 int closed_right,
+                                 const void* dA, int dA_dtype, int acc_area,
+                                 const void* const* integrands, const int* integrand_dtypes,
+                                 int n_int, const uint8_t* q_mask,
+                                 int scan_mode, const int32_t* decreasing,
+                                 double* pdf, double* cdf, int32_t* bin_idx,
+                                 void* workspace, size_t ws_bytes, void* stream)
+{
+    XC_REQUIRE(cdf, "xc_bin_accumulate: null pointer");
+    const int K = (acc_area ? 1 : 0) + n_int;
+    ScanOut so;
+    for (int k = 0; k < 4; ++k) so.p[k] = cdf + (size_t)k * N;
+    so.stride = (long)K * N;
+    return bin_accumulate_impl(q, q_dtype, S, P, edges, edges_stride, N, closed_right, dA, dA_dtype,
+                               acc_area, integrands, integrand_dtypes, n_int, q_mask, scan_mode,
+                               decreasing, pdf, so, bin_idx, workspace, ws_bytes, stream);
+}
+
+int xc::bin_accumulate_impl(const void* q, int q_dtype, long S, long P,
+                            const double* edges, long edges_stride, int N,
+                            int closed_right,
+                            const void* dA, int dA_dtype, int acc_area,
+                            const void* const* integrands, const int* integrand_dtypes,
+                            int n_int, const uint8_t* q_mask,
+                            int scan_mode, const int32_t* decreasing,
+                            double* pdf, const ScanOut& so, int32_t* bin_idx,
+                            void* workspace, size_t ws_bytes, void* stream)
+{
+    XC_REQUIRE(q && edges && dA, "xc_bin_accumulate: null pointer");
+    XC_REQUIRE(S > 0 && P > 0 && N >= 1, "xc_bin_accumulate: need S>0, P>0, N>=1");
+    XC_REQUIRE(q_dtype == XC_F32 || q_dtype == XC_F64, "xc_bin_accumulate: bad q dtype");
+    XC_REQUIRE(n_int >= 0 && n_int <= XC_MAX_INTEGRANDS, "xc_bin_accumulate: n_int out of range");
+    XC_REQUIRE(edges_stride == 0 || edges_stride == N + 1, "xc_bin_accumulate: edges_stride must be 0 or N+1");
+    const int K = (acc_area ? 1 : 0) + n_int;
+    XC_REQUIRE(K >= 1 && K <= 4, "xc_bin_accumulate: nothing to accumulate");
+    HistPlan pl = plan_hist(S, P, N, K);
+    XC_REQUIRE(pl.ncopy >= 1, "xc_bin_accumulate: N=%d with K=%d does not fit shared memory", N, K);
+    XC_REQUIRE(workspace && ws_bytes >= xc_bin_accumulate_workspace_bytes(S, P, N, K),
+               "xc_bin_accumulate: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    Arena ar(workspace, ws_bytes);
+    HistParams hp;
+    hp.q = q; hp.P = P; hp.per = ((P + pl.C - 1) / pl.C + 3) & ~3L;
+    hp.edges = edges; hp.edges_stride = edges_stride; hp.N = N; hp.closed_right = closed_right;
+    hp.dA = dA; hp.dA_f32 = dA_dtype == XC_F32; hp.acc_area = acc_area;
+    hp.n_int = n_int;
+    for (int n = 0; n < XC_MAX_INTEGRANDS; ++n) {
+        hp.integ[n] = n < n_int ? integrands[n] : nullptr;
+        hp.integ_f32[n] = n < n_int ? (integrand_dtypes[n] == XC_F32) : 0;
+        XC_REQUIRE(n >= n_int || hp.integ[n], "xc_bin_accumulate: null integrand");
+    }
+    hp.q_mask = q_mask;
+    hp.part = ar.take<double>((size_t)S * pl.C * K * N);
+    hp.bin_idx = bin_idx;
+    hp.ncopy = pl.ncopy;
+    for (long s0 = 0; s0 < S; s0 += 65535) {
+        long ns = S - s0 < 65535 ? S - s0 : 65535;
+        hp.s0 = s0;
+        int rc;
+        if (q_dtype == XC_F32) {
+            rc = K == 1 ? launch_hist<float, 1>(hp, pl, ns, st) : K == 2 ? launch_hist<float, 2>(hp, pl, ns, st)
+               : K == 3 ? launch_hist<float, 3>(hp, pl, ns, st) : launch_hist<float, 4>(hp, pl, ns, st);
+        } else {
+            rc = K == 1 ? launch_hist<double, 1>(hp, pl, ns, st) : K == 2 ? launch_hist<double, 2>(hp, pl, ns, st)
+               : K == 3 ? launch_hist<double, 3>(hp, pl, ns, st) : launch_hist<double, 4>(hp, pl, ns, st);
+        }
+        if (rc) return rc;
+    }
+    XC_REQUIRE(S <= 0x7fffffffL, "xc_bin_accumulate: too many slices");
+    dim3 g2((unsigned)S, (unsigned)K);
+    XC_REQUIRE((size_t)N * 8 <= 200 * 1024, "xc_bin_accumulate: N too large for the scan kernel");
+    if ((size_t)N * 8 > 48 * 1024)
+        XC_CUDA_OK(cudaFuncSetAttribute(k_reduce_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)N * 8)));
+    k_reduce_scan<<<g2, 256, (size_t)N * 8, st>>>(hp.part, pl.C, K, N, scan_mode, decreasing, pdf, so);
+    XC_LAUNCH_OK();
+    return 0;
+}

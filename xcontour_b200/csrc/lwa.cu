@@ -1,0 +1,395 @@
+// Kernel (4): local wave activity / local APE column integrals
+// (Contour2D.cal_local_wave_activity, xcontour/core.py:696-799; cal_local_APE,
+// core.py:908-942; cal_local_wave_activity2, core.py:802-905).
+//
+// The reference loops over every row j of the equivalent dimension and reduces a
+// masked full slice each time: O(n_eq^2 * n_x).  For a profile Q that is sorted
+// in the direction `increase` implies, every cell (j', i) contributes
+// sign*(v - Q_j)*w to ONE contiguous j-range of its own column,
+//     j' < j < lo(v)      when lo(v) = #{Q < v} > j'+1     (mask -1 region)
+//     hi(v) <= j <= j'    when hi(v) = #{Q <= v} <= j'     (mask +1 region)
+// so a column is two difference arrays (sum w, sum w*v) followed by one prefix
+// sum:  LWA[j] = V[j] - Q_j * S[j].   One warp owns one column (difference
+// arrays in shared memory, lanes walk 32 rows at a time); lo/hi come from a
+// 2048-bucket lookup table over Q plus a short exact search.  The slot j'+1 of
+// each cell is written without conflicts; the other end of the range is a
+// warp-private scatter resolved with the same byte-tag protocol as hist.cu.
+// Profiles that are not sorted (or contain NaN) take the exact O(n_eq^2) kernel.
+#include "common.cuh"
+#include <math_constants.h>
+
+namespace xc {
+
+constexpr int LWA_LUT = 2048;
+constexpr int LWA_MAX_TC = 16;
+
+__global__ void k_check_sorted(const double* __restrict__ Q, int ny, int increase,
+                               int32_t* __restrict__ flag)
+{
+    const long s = blockIdx.x;
+    const double sg = increase ? 1.0 : -1.0;
+    const double* Qs = Q + s * ny;
+    int bad = 0;
+    for (int j = threadIdx.x; j < ny; j += blockDim.x) {
+        double a = sg * Qs[j];
+        if (isnan(a)) bad = 1;
+        if (j + 1 < ny && !(a <= sg * Qs[j + 1])) bad = 1;
+    }
+    bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) flag[s] = bad ? 0 : 1;
+}
+
+struct LwaSmem {
+    size_t off_Q, off_D, off_lut, off_tag, off_sq, off_sw, total;
+    int nyp, tagp;
+};
+static __host__ __device__ inline LwaSmem lwa_layout(int ny, int TC)
+{
+    LwaSmem L;
+    L.nyp = ny + 2;
+    L.tagp = (ny + 2 + 15) & ~15;
+    size_t o = 0;
+    L.off_Q = o;   o += (size_t)((ny + 1) & ~1) * 8;
+    L.off_D = o;   o += (size_t)TC * L.nyp * 16;
+    L.off_sq = o;  o += (size_t)32 * (TC + 1) * 8;
+    L.off_sw = o;  o += (size_t)32 * (TC + 1) * 8;
+    L.off_lut = o; o += (size_t)(LWA_LUT + 2) * 2;
+    o = (o + 15) & ~(size_t)15;
+    L.off_tag = o; o += (size_t)TC * L.tagp;
+    L.total = o;
+    return L;
+}
+
+__device__ __forceinline__ int lwa_bucket(double v, double qmin, double scale)
+{
+    double t = (v - qmin) * scale;
+    int b = (int)fmin(t, (double)(LWA_LUT - 1));
+    return b < 0 ? 0 : b;
+}
+
+// grid = (ceil(nx/TC), nslices), block = TC warps.
+template <typename QT>
+__global__ void __launch_bounds__(LWA_MAX_TC * 32)
+k_lwa_fast(const QT* __restrict__ q, long s0, int ny, int nx,
+           const double* __restrict__ Qref, const double* __restrict__ ww,
+           int increase, int part, const int32_t* __restrict__ sorted,
+           double* __restrict__ out, int TC)
+{
+    const long s = s0 + blockIdx.y;
+    if (!sorted[s]) return;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const LwaSmem L = lwa_layout(ny, TC);
+    double*   Qs  = reinterpret_cast<double*>(smem + L.off_Q);
+    double2*  D   = reinterpret_cast<double2*>(smem + L.off_D);
+    double*   sq  = reinterpret_cast<double*>(smem + L.off_sq);    // [32][TC+1]
+    double*   sw  = reinterpret_cast<double*>(smem + L.off_sw);
+    uint16_t* lut = reinterpret_cast<uint16_t*>(smem + L.off_lut);
+    uint8_t*  tag = smem + L.off_tag;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
+    const double sg = increase ? 1.0 : -1.0;
+    const int i0 = blockIdx.x * TC;
+    const QT* qs = q + s * (long)ny * nx;
+    const double* Qg = Qref + s * (long)ny;
+
+    for (int j = tid; j < ny; j += nthr) Qs[j] = sg * Qg[j];
+    for (int k = tid; k < TC * L.nyp; k += nthr) D[k] = make_double2(0.0, 0.0);
+    __syncthreads();
+    const double qmin = Qs[0], qmax = Qs[ny - 1];
+    const double scale = (qmax > qmin) ? (double)LWA_LUT / (qmax - qmin) : 0.0;
+    // lut[b] = first j whose bucket is >= b; buckets are monotone in Q
+    for (int j = tid; j <= ny; j += nthr) {
+        int bj = (j < ny) ? lwa_bucket(Qs[j], qmin, scale) : LWA_LUT;
+        int bp = (j > 0) ? lwa_bucket(Qs[j - 1], qmin, scale) : -1;
+        for (int b = bp + 1; b <= bj; ++b) lut[b] = (uint16_t)j;
+    }
+    // (the sync after the first staging store below also covers the lut)
+
+    // which mask regions are integrated (core.py:773-784)
+    const bool keep_pos = (part == XC_PART_UPPER) == (increase != 0);
+    const bool use_t1 = (part == XC_PART_ALL) || !keep_pos;   // mask -1 region
+    const bool use_t2 = (part == XC_PART_ALL) || keep_pos;    // mask +1 region
+
+    // staging map: thread -> (row rr, column cc) of a 32 x TC chunk
+    const int rr = tid / TC, cc = tid - rr * TC;
+    const bool col_ok = (i0 + cc) < nx;
+    auto fetch = [&](int r0, double& vq, double& vw) {
+        const int j = r0 + rr;
+        if (rr < 32 && j < ny && col_ok) {
+            vq = sg * (double)__ldg(qs + (long)j * nx + i0 + cc);
+            vw = __ldg(ww + (long)j * nx + i0 + cc);
+        } else { vq = CUDART_NAN; vw = 0.0; }
+    };
+    double nq, nw;
+    fetch(0, nq, nw);
+    double2* Dw = D + (size_t)warp * L.nyp;
+    uint8_t* tagw = tag + (size_t)warp * L.tagp;
+
+    for (int r0 = 0; r0 < ny; r0 += 32) {
+        if (rr < 32) { sq[rr * (TC + 1) + cc] = nq; sw[rr * (TC + 1) + cc] = nw; }
+        __syncthreads();
+        if (r0 + 32 < ny) fetch(r0 + 32, nq, nw);          // prefetch the next chunk
+        const int jp = r0 + lane;
+        const double v = sq[lane * (TC + 1) + warp];
+        const double w = sw[lane * (TC + 1) + warp];
+        bool act = (jp < ny) && !isnan(v) && !isnan(w);
+        int target = 0;
+        if (act) {
+            int lo;
+            if (v < qmin) lo = 0;
+            else if (v > qmax) lo = ny;
+            else {
+                const int b = lwa_bucket(v, qmin, scale);
+                int a = lut[b], e = lut[b + 1];
+                while (a < e) {                              // first idx with Qs >= v
+                    int mid = (a + e) >> 1;
+                    if (Qs[mid] < v) a = mid + 1; else e = mid;
+                }
+                lo = a;
+            }
+            if (lo > jp + 1) { target = lo; act = use_t1; }
+            else {
+                int hi = lo;
+                while (hi < ny && Qs[hi] == v) ++hi;
+                if (hi <= jp) { target = hi; act = use_t2; }
+                else act = false;
+            }
+        }
+        const double wv = w * v;
+        if (act) {                                           // own slot j'+1: +(w, w v)
+            double2 t = Dw[jp + 1]; t.x += w; t.y += wv; Dw[jp + 1] = t;
+        }
+        __syncwarp();
+        {                                                    // far end: -(w, w v)
+            unsigned pending = __ballot_sync(XC_FULL, act);
+            while (pending) {
+                if (act) tagw[target] = (uint8_t)lane;
+                __syncwarp();
+                if (act && tagw[target] == (uint8_t)lane) {
+                    double2 t = Dw[target]; t.x -= w; t.y -= wv; Dw[target] = t;
+                    act = false;
+                }
+                __syncwarp();
+                pending = __ballot_sync(XC_FULL, act);
+            }
+        }
+        __syncthreads();                                     // staging buffers are reused
+    }
+
+    // prefix sums down each column, 32 rows per step, then a coalesced store
+    double cS = 0.0, cV = 0.0;
+    double* so = sq;                                         // [32][TC+1] output staging
+    for (int r0 = 0; r0 < ny; r0 += 32) {
+        const int j = r0 + lane;
+        double2 d = (j < ny) ? Dw[j] : make_double2(0.0, 0.0);
+        double xs = d.x, xv = d.y;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            double ts = __shfl_up_sync(XC_FULL, xs, o), tv = __shfl_up_sync(XC_FULL, xv, o);
+            if (lane >= o) { xs += ts; xv += tv; }
+        }
+        xs += cS; xv += cV;
+        cS = __shfl_sync(XC_FULL, xs, 31); cV = __shfl_sync(XC_FULL, xv, 31);
+        if (j < ny) so[lane * (TC + 1) + warp] = sg * (xv - Qs[j] * xs);
+        __syncthreads();
+        if (rr < 32 && r0 + rr < ny && col_ok)
+            out[(s * ny + r0 + rr) * (long)nx + i0 + cc] = so[rr * (TC + 1) + cc];
+        __syncthreads();
+    }
+}
+
+// Exact reference loop (any profile, both variants).  Persistent grid: each CTA
+// walks (slice, tile) work items; slices already handled by k_lwa_fast are
+// skipped.  block = (32, 8): 32 columns x 8 output rows.
+template <typename QT>
+__global__ void __launch_bounds__(256)
+k_lwa_brute(const QT* __restrict__ q, long S, int ny, int nx,
+            const double* __restrict__ Qref, const double* __restrict__ ww,
+            int increase, int part, int variant, const int32_t* __restrict__ skip,
+            double* __restrict__ out)
+{
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tiles_x = (nx + 31) / 32, tiles_y = (ny + 7) / 8;
+    const long tiles = (long)tiles_x * tiles_y;
+    const bool f = variant == 1 ? (increase != 0) : (increase == 0);   // core.py:759 / 865
+    const bool keep_pos = (part == XC_PART_UPPER) == (increase != 0);
+    for (long s = 0; s < S; ++s) {
+        if (skip && skip[s]) continue;
+        const QT* qs = q + s * (long)ny * nx;
+        const double* Qs = Qref + s * (long)ny;
+        for (long t = blockIdx.x; t < tiles; t += gridDim.x) {
+            const int i = (int)(t % tiles_x) * 32 + tx;
+            const int j = (int)(t / tiles_x) * 8 + ty;
+            if (i >= nx || j >= ny) continue;
+            const double Qj = Qs[j];
+            const double qj = (double)__ldg(qs + (long)j * nx + i);
+            double acc = 0.0;
+            for (int jp = 0; jp < ny; ++jp) {
+                const double qe = variant == 1
+                    ? (double)__ldg(qs + (long)jp * nx + i) - Qj
+                    : qj - Qs[jp];
+                const bool m = jp >= j;
+                int mask = 0;
+                if (f) { if (qe > 0.0 && !m) mask = -1; else if (qe < 0.0 && m) mask = 1; }
+                else   { if (qe < 0.0 && !m) mask = -1; else if (qe > 0.0 && m) mask = 1; }
+                if (part != XC_PART_ALL && ((mask > 0) != keep_pos)) mask = 0;
+                if (mask != 0) {
+                    double term = qe * (double)mask * __ldg(ww + (long)jp * nx + i);
+                    if (!isnan(term)) acc += term;
+                }
+            }
+            out[(s * ny + j) * (long)nx + i] = -acc;
+        }
+    }
+}
+
+template <typename QT>
+__global__ void k_lwa_mask(const QT* __restrict__ q, long total, int ny, int nx,
+                           const double* __restrict__ Qref, int j, int increase,
+                           int variant, int8_t* __restrict__ mask)
+{
+    const bool f = variant == 1 ? (increase != 0) : (increase == 0);
+    const long plane = (long)ny * nx;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long)gridDim.x * blockDim.x) {
+        const long s = idx / plane; const long r = idx - s * plane;
+        const int jp = (int)(r / nx); const int i = (int)(r - (long)jp * nx);
+        const double* Qs = Qref + s * (long)ny;
+        const double qe = variant == 1 ? (double)q[idx] - Qs[j]
+                                       : (double)q[s * plane + (long)j * nx + i] - Qs[jp];
+        const bool m = jp >= j;
+        int8_t mk = 0;
+        if (f) { if (qe > 0.0 && !m) mk = -1; else if (qe < 0.0 && m) mk = 1; }
+        else   { if (qe < 0.0 && !m) mk = -1; else if (qe > 0.0 && m) mk = 1; }
+        mask[idx] = mk;
+    }
+}
+
+// ---- ww = (dA/max(dA)) * dA ------------------------------------------------
+__global__ void k_max_partial(const void* __restrict__ dA, int is_f32, long P, double* __restrict__ part)
+{
+    double mx = -CUDART_INF;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < P; i += (long)gridDim.x * blockDim.x)
+        mx = fmax(mx, ld_as_f64(dA, i, is_f32));
+    mx = warp_max(mx);
+    __shared__ double sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) mx = fmax(mx, sm[k]);
+        part[blockIdx.x] = mx;
+    }
+}
+__global__ void k_lwa_weights(const void* __restrict__ dA, int is_f32, long P,
+                              const double* __restrict__ part, int nparts, double* __restrict__ ww)
+{
+    double mx = -CUDART_INF;
+    for (int k = 0; k < nparts; ++k) mx = fmax(mx, part[k]);
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < P; i += (long)gridDim.x * blockDim.x) {
+        if (is_f32) {
+            float a = ((const float*)dA)[i];
+            float wei = __fdiv_rn(a, (float)mx);             // rounded in dA's dtype
+            ww[i] = __dmul_rn((double)wei, (double)a);
+        } else {
+            double a = ((const double*)dA)[i];
+            ww[i] = __dmul_rn(__ddiv_rn(a, mx), a);
+        }
+    }
+}
+
+}  // namespace xc
+
+using namespace xc;
+
+static int lwa_pick_tc(int ny)
+{
+    for (int tc = LWA_MAX_TC; tc >= 1; --tc)
+        if (lwa_layout(ny, tc).total <= 227 * 1024) return tc;
+    return 0;
+}
+
+extern "C" size_t xc_lwa_weights_workspace_bytes(long P) { (void)P; return 256 + 256 * sizeof(double); }
+
+extern "C" int xc_lwa_weights(const void* dA, int dA_dtype, long P, double* ww,
+                              void* workspace, size_t ws_bytes, void* stream)
+{
+    XC_REQUIRE(dA && ww && P > 0, "xc_lwa_weights: bad arguments");
+    XC_REQUIRE(workspace && ws_bytes >= xc_lwa_weights_workspace_bytes(P), "xc_lwa_weights: workspace too small");
+    Arena ar(workspace, ws_bytes);
+    double* part = ar.take<double>(256);
+    cudaStream_t st = (cudaStream_t)stream;
+    int nb = (int)((P + 255) / 256); if (nb > 256) nb = 256;
+    k_max_partial<<<nb, 256, 0, st>>>(dA, dA_dtype == XC_F32, P, part);
+    XC_LAUNCH_OK();
+    k_lwa_weights<<<nb, 256, 0, st>>>(dA, dA_dtype == XC_F32, P, part, nb, ww);
+    XC_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" size_t xc_lwa_workspace_bytes(long S) { return 256 + (size_t)(S > 0 ? S : 0) * sizeof(int32_t); }
+
+extern "C" int xc_lwa(const void* q, int q_dtype, long S, int n_eq, int n_x,
+                      const double* Qref, const double* ww,
+                      int increase, int part, int variant,
+                      double* out, void* workspace, size_t ws_bytes, void* stream)
+{
+    XC_REQUIRE(q && Qref && ww && out, "xc_lwa: null pointer");
+    XC_REQUIRE(S > 0 && n_eq >= 1 && n_x >= 1, "xc_lwa: need S>0, n_eq>=1, n_x>=1");
+    XC_REQUIRE(q_dtype == XC_F32 || q_dtype == XC_F64, "xc_lwa: bad dtype");
+    XC_REQUIRE(part >= XC_PART_ALL && part <= XC_PART_LOWER,
+               "invalid part, should be in ['all', 'upper', 'lower']");
+    XC_REQUIRE(variant == 1 || variant == 2, "xc_lwa: variant must be 1 or 2");
+    XC_REQUIRE(workspace && ws_bytes >= xc_lwa_workspace_bytes(S), "xc_lwa: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    Arena ar(workspace, ws_bytes);
+    int32_t* sorted = ar.take<int32_t>((size_t)S);
+    const int tc = (n_eq < 65535) ? lwa_pick_tc(n_eq) : 0;
+    const bool fast = (variant == 1) && tc >= 1;
+    if (fast) {
+        k_check_sorted<<<(unsigned)S, 256, 0, st>>>(Qref, n_eq, increase, sorted);
+        XC_LAUNCH_OK();
+        const LwaSmem L = lwa_layout(n_eq, tc);
+        if (q_dtype == XC_F32)
+            XC_CUDA_OK(cudaFuncSetAttribute(k_lwa_fast<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+        else
+            XC_CUDA_OK(cudaFuncSetAttribute(k_lwa_fast<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+        for (long s0 = 0; s0 < S; s0 += 65535) {
+            long ns = S - s0 < 65535 ? S - s0 : 65535;
+            dim3 grid((unsigned)((n_x + tc - 1) / tc), (unsigned)ns);
+            if (q_dtype == XC_F32)
+                k_lwa_fast<float><<<grid, tc * 32, L.total, st>>>((const float*)q, s0, n_eq, n_x, Qref, ww,
+                                                                  increase, part, sorted, out, tc);
+            else
+                k_lwa_fast<double><<<grid, tc * 32, L.total, st>>>((const double*)q, s0, n_eq, n_x, Qref, ww,
+                                                                   increase, part, sorted, out, tc);
+            XC_LAUNCH_OK();
+        }
+    }
+    // exact loop for whatever the fast path did not take
+    dim3 blk(32, 8);
+    unsigned nb = (unsigned)(sm_count() * 8);
+    if (q_dtype == XC_F32)
+        k_lwa_brute<float><<<nb, blk, 0, st>>>((const float*)q, S, n_eq, n_x, Qref, ww, increase, part,
+                                               variant, fast ? sorted : nullptr, out);
+    else
+        k_lwa_brute<double><<<nb, blk, 0, st>>>((const double*)q, S, n_eq, n_x, Qref, ww, increase, part,
+                                                variant, fast ? sorted : nullptr, out);
+    XC_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int xc_lwa_mask(const void* q, int q_dtype, long S, int n_eq, int n_x,
+                           const double* Qref, int j, int increase, int variant,
+                           int8_t* mask, void* stream)
+{
+    XC_REQUIRE(q && Qref && mask, "xc_lwa_mask: null pointer");
+    XC_REQUIRE(j >= 0 && j < n_eq, "indices in mask_idx out of boundary");
+    const long total = S * (long)n_eq * n_x;
+    long b = (total + 255) / 256; long cap = (long)sm_count() * 16; if (b > cap) b = cap;
+    if (q_dtype == XC_F32)
+        k_lwa_mask<float><<<(unsigned)b, 256, 0, (cudaStream_t)stream>>>((const float*)q, total, n_eq, n_x, Qref, j, increase, variant, mask);
+    else
+        k_lwa_mask<double><<<(unsigned)b, 256, 0, (cudaStream_t)stream>>>((const double*)q, total, n_eq, n_x, Qref, j, increase, variant, mask);
+    XC_LAUNCH_OK();
+    return 0;
+}

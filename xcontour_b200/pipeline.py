@@ -1,0 +1,181 @@
+"""
+Batched Keff + LWA over many independent slices -- the workload of
+BASELINE.json (config 4: 721x1440 tracer, 361 contours) -- and its sharding over
+the GPUs of one box.
+
+The per-slice call chain is exactly the reference workflow of
+tests/test_Keff_atmos.py:76-92 + tests/test_LWA.py:57-77:
+
+    ctr   = cal_contours(N)                              core.py:205
+    table = cal_area_eqCoord_table_hist(mask)            core.py:150   (once)
+    area, intgrdS = cal_integral_within_contours_hist    core.py:412
+    latEq = table.lookup_coordinates(area)               core.py:1136
+    Lmin, dintSdA, dqdA, Leq2, nkeff                     utils.py:518, core.py:463-966
+    Q     = interp_to_coords(lat, latEq, ctr)            core.py:1050
+    LWA   = cal_local_wave_activity(q, Q)                core.py:696
+
+run on the device for a whole batch with one C-ABI call (xc_keff_lwa_batch).
+Slices are independent, so multi-GPU = contiguous slice ranges per rank and one
+gather of the small contour-space results; the LWA fields stay
+sharded.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from ._lib import KeffLwaArgs, PART, SCAN_PREFIX, SCAN_TOTAL_MINUS, XC_F32, XC_F64, check
+
+CONTOUR_VARS = ("ctr", "area", "intgrdS", "latEq", "Lmin", "dintSdA", "dqdA", "Leq2", "nkeff")
+
+
+def slice_range(S, rank, world):
+    """Contiguous block of ceil(S/world) slice indices owned by ``rank``."""
+    per = (S + world - 1) // world
+    lo = min(S, rank * per)
+    return lo, min(S, lo + per)
+
+
+class KeffLwaPlan(object):
+    """Static (time-independent) part of the workflow: grid metrics, the A(Yeq)
+    table, LWA weights -- built once, reused for every batch."""
+
+    def __init__(self, lat_deg, lon_deg, dA, N, increase=True, lt=True,
+                 dtype=np.float32, keff_mask=1e5, part="all", mask=None):
+        ops.require_cuda()
+        lat = np.asarray(lat_deg)
+        lon = np.asarray(lon_deg)
+        self.ny, self.nx, self.N = lat.shape[0], lon.shape[0], int(N)
+        self.increase, self.lt = bool(increase), bool(lt)
+        self.ctr_dtype = XC_F32 if np.dtype(dtype) == np.float32 else XC_F64
+        self.keff_mask, self.part = float(keff_mask), PART[part]
+        dA = np.ascontiguousarray(np.broadcast_to(np.asarray(dA), (self.ny, self.nx)))
+        self.dA = ops.to_dev(dA)
+        self.ww = ops.lwa_weights(self.dA.reshape(-1))
+        # A(Yeq) table exactly as Contour2D.cal_area_eqCoord_table_hist builds it
+        fdt = lat.dtype if lat.dtype in (np.float32, np.float64) else np.float64
+        ctrVar = np.ascontiguousarray(np.broadcast_to(lat.astype(fdt)[:, None], (self.ny, self.nx)))
+        yIncre = not (lat[-1] < lat[0])
+        ylt = self.lt if self.increase == yIncre else (not self.lt)
+        edges, _ = ops.hist_edges(ops.to_dev(lat.astype(np.float64).reshape(1, -1)),
+                                  XC_F32 if fdt == np.float32 else XC_F64, time_branch=False)
+        m = np.ones((self.ny, self.nx), np.uint8) if mask is None else (np.asarray(mask) == 1).astype(np.uint8)
+        cdf, _, _ = ops.bin_accumulate(ops.to_dev(ctrVar).reshape(1, -1), edges[0], self.dA.reshape(-1),
+                                       acc_area=True, q_mask=ops.to_dev(m.reshape(-1)),
+                                       scan_mode=SCAN_PREFIX if ylt else SCAN_TOTAL_MINUS)
+        self.table = cdf[0, 0].contiguous()
+        self.table_coord = ops.to_dev((lat if yIncre else lat[::-1]).astype(np.float64))
+        # coordinates Q is interpolated to: tracer.latitude.astype(dtype) (tests/test_LWA.py:72)
+        self.eq_coord = ops.to_dev(lat.astype(dtype).astype(np.float64))
+        self.lat_rad = ops.to_dev(np.deg2rad(lat.astype(np.float64)))
+        lam = np.deg2rad(lon.astype(np.float64))
+        self.dlambda = float(lam[1] - lam[0])
+
+    def workspace_bytes(self, S):
+        return _lib.load().xc_keff_lwa_batch_workspace_bytes(S, self.ny, self.nx, self.N)
+
+    def alloc_outputs(self, S, lwa=True):
+        dev = self.dA.device
+        out = {k: torch.empty((S, self.N), dtype=torch.float64, device=dev) for k in CONTOUR_VARS}
+        out["Qref"] = torch.empty((S, self.ny), dtype=torch.float64, device=dev)
+        if lwa:
+            out["lwa"] = torch.empty((S, self.ny, self.nx), dtype=torch.float64, device=dev)
+        return out
+
+    def run(self, q, grdS=None, out=None, ws=None):
+        """q[S, ny, nx] (fp32/fp64, on the GPU) -> dict of device tensors.
+        grdS=None computes |grad q|^2 on the fly with the lat-lon stencil."""
+        lib = ops.require_cuda()
+        S = q.shape[0]
+        assert q.is_cuda and q.is_contiguous() and tuple(q.shape[1:]) == (self.ny, self.nx)
+        if out is None:
+            out = self.alloc_outputs(S)
+        nb = self.workspace_bytes(S)
+        if ws is None:
+            ws = ops.workspace(nb, tag="fused")
+        a = KeffLwaArgs()
+        a.q, a.q_dtype = q.data_ptr(), ops.fdtype(q)
+        a.S, a.n_y, a.n_x, a.N = S, self.ny, self.nx, self.N
+        a.increase, a.lt, a.ctr_dtype = int(self.increase), int(self.lt), self.ctr_dtype
+        a.dA, a.dA_dtype = self.dA.data_ptr(), ops.fdtype(self.dA)
+        if grdS is not None:
+            a.grdS, a.grdS_dtype = grdS.data_ptr(), ops.fdtype(grdS)
+        else:
+            a.grdS, a.grdS_dtype = None, XC_F64
+        a.lat_rad, a.dlambda = self.lat_rad.data_ptr(), self.dlambda
+        a.table, a.table_coord, a.n_table = self.table.data_ptr(), self.table_coord.data_ptr(), self.ny
+        a.eq_coord, a.ww = self.eq_coord.data_ptr(), self.ww.data_ptr()
+        a.keff_mask, a.part = self.keff_mask, self.part
+        for k in CONTOUR_VARS:
+            setattr(a, k, out[k].data_ptr() if k in out else None)
+        a.Qref = out["Qref"].data_ptr() if "Qref" in out else None
+        a.lwa = out["lwa"].data_ptr() if "lwa" in out else None
+        check(lib.xc_keff_lwa_batch(ctypes.byref(a), ctypes.c_void_p(ws.data_ptr()), nb, ops.stream_ptr()))
+        return out
+
+
+class HostStreamer(object):
+    """End-to-end driver for HOST-resident tracers: pinned host slices ->
+    (H2D, fused batch, D2H of every result) with two buffers in flight so the
+    copies of batch i+1 / i-1 overlap the kernels of batch i."""
+
+    def __init__(self, plan, batch, q_dtype=torch.float32, copy_lwa=True):
+        self.plan, self.batch, self.copy_lwa = plan, int(batch), copy_lwa
+        dev = plan.dA.device
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        self.qdev = [torch.empty((batch, plan.ny, plan.nx), dtype=q_dtype, device=dev) for _ in range(2)]
+        self.outs = [plan.alloc_outputs(batch) for _ in range(2)]
+        self.ws = [torch.empty(plan.workspace_bytes(batch), dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.host = [{k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in o.items()
+                      if copy_lwa or k != "lwa"} for o in self.outs]
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def run(self, q_host, consume=None):
+        """q_host: pinned CPU tensor [S, ny, nx].  ``consume(s0, s1, host_dict)`` is
+        called for every finished batch (host buffers are reused afterwards)."""
+        S = q_host.shape[0]
+        pending = [None, None]
+        nb = (S + self.batch - 1) // self.batch
+        for b in range(nb + 2):
+            i = b % 2
+            if pending[i] is not None:                    # drain the batch that used buffer i
+                s0, s1, ev = pending[i]
+                ev.synchronize()
+                if consume is not None:
+                    consume(s0, s1, {k: v[:s1 - s0] for k, v in self.host[i].items()})
+                pending[i] = None
+            if b >= nb:
+                continue
+            s0, s1 = b * self.batch, min(S, (b + 1) * self.batch)
+            n = s1 - s0
+            with torch.cuda.stream(self.streams[i]):
+                self.qdev[i][:n].copy_(q_host[s0:s1], non_blocking=True)
+                self.h2d_bytes += q_host[s0:s1].numel() * q_host.element_size()
+                out = {k: v[:n] for k, v in self.outs[i].items()}
+                self.plan.run(self.qdev[i][:n], out=out, ws=self.ws[i])
+                for k, hv in self.host[i].items():
+                    hv[:n].copy_(out[k], non_blocking=True)
+                    self.d2h_bytes += out[k].numel() * out[k].element_size()
+                ev = torch.cuda.Event()
+                ev.record(self.streams[i])
+            pending[i] = (s0, s1, ev)
+
+
+def gather_contour_space(local, S_total, group=None):
+    """All-gather the contour-space results ([S_local, N] each) of every rank into
+    [S_total, N] tensors.  Works on NCCL (CUDA tensors) and gloo (CPU tensors);
+    ranks own contiguous ``slice_range`` blocks, padded to equal length for the
+    collective.  This is the only communication of the whole path."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    per = (S_total + world - 1) // world
+    out = {}
+    for k, v in local.items():
+        pad = torch.zeros((per,) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device)
+        pad[:v.shape[0]] = v
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad, group=group)
+        out[k] = torch.cat(parts, dim=0)[:S_total]
+    return out
