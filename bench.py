@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""
+bench.py -- slices/sec for Keff + LWA at 721x1440 (BASELINE.json config 4:
+ERA5-scale tracer, 361 equally spaced contours) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path (levels -> binning/CDFs with in-flight
+|grad q|^2 -> Keff epilogue -> Q(lat) -> LWA, one xc_keff_lwa_batch call) over a
+batch of synthetic slices per GPU.  Independent slices shard across ranks with no
+data-path collective ("weak" scaling: per-GPU work is fixed).
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for how every
+field is obtained.  `--impl reference` times the restated reference algorithm
+(oracle/, NumPy, all host cores) on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+NY, NX, NLEV = 721, 1440, 361
+P = NY * NX
+ALG_BYTES_PER_SLICE = P * 4 + P * 8          # one fp32 read of q + the fp64 LWA store
+STAGE_ALG_BYTES = {                          # per slice, compulsory traffic of each stage
+    "minmax_levels": P * 4,                  # read q
+    "bin_accumulate": P * 4,                 # read q (dA / edges are L2-resident, shared)
+    "lwa": P * 4 + P * 8,                    # read q, write LWA (fp64)
+}
+METRIC = "keff_lwa_slices_per_sec_721x1440"
+
+
+def grid():
+    lat = np.linspace(-90.0, 90.0, NY).astype(np.float32)
+    lon = (np.arange(NX) * (360.0 / NX)).astype(np.float32)
+    return lat, lon
+
+
+def synth_slice_np(idx, lat, lon):
+    """q = sin(phi) + 0.3 cos^2(phi) sin(6 lam + 3 phi + phase) + 0.02 N(0,1)."""
+    rng = np.random.default_rng(1234 + idx)
+    phi, lam = np.deg2rad(lat.astype(np.float64))[:, None], np.deg2rad(lon.astype(np.float64))[None, :]
+    phase = 2 * np.pi * rng.random()
+    return (np.sin(phi) + 0.3 * np.cos(phi) ** 2 * np.sin(6 * lam + 3 * phi + phase)
+            + 0.02 * rng.standard_normal((NY, NX))).astype(np.float32)
+
+
+def peak_hbm():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# ----------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle (NumPy restatement), all host cores
+# ----------------------------------------------------------------------------
+def _cpu_worker(args):
+    idx, nrows = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from oracle import xcontour_oracle as O
+    lat, lon = grid()
+    q = synth_slice_np(idx, lat, lon)[None]
+    dA = O.latlon_cell_area(lat, lon).astype(np.float32)
+    t0 = time.perf_counter()
+    ctr = O.cal_contours(q, NLEV, True)
+    grd = O.squared_gradient_latlon(q, lat, lon)
+    tbl, c = O.cal_area_eqCoord_table_hist(lat, np.ones((NY, NX), np.float32), dA, 0, True, True)
+    area = O.cal_integral_within_contours_hist(q, ctr, dA, True)
+    intg = O.cal_integral_within_contours_hist(q, ctr, dA, True, integrand=grd)
+    latEq = O.table_lookup_coordinates(area, tbl, c)
+    with np.errstate(all="ignore"):
+        Lmin = O.latitude_lengths_at(latEq)
+        Leq2 = O.cal_sqared_equivalent_length(O.cal_gradient_wrt_area(intg, area),
+                                              O.cal_gradient_wrt_area(ctr, area))
+        O.cal_normalized_Keff(Leq2, Lmin)
+    Q = O.interp_to_coords(lat, latEq, ctr)
+    t1 = time.perf_counter()
+    rows = np.linspace(0, NY - 1, nrows).astype(int).tolist()
+    O.cal_local_wave_activity(q, Q, dA, lat, True, rows=rows)      # the reference's j-loop
+    t2 = time.perf_counter()
+    return t1 - t0, (t2 - t1) * NY / float(nrows)
+
+
+def cpu_sample(nrows=24, per_core=1, cores=None):
+    """One bounded sample: `per_core` slices per core, Keff in full, the LWA j-loop
+    on `nrows` of the 721 rows (cost is uniform in j) extrapolated to 721."""
+    cores = cores or os.cpu_count() or 1
+    n = cores * per_core
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(i, nrows) for i in range(n)])
+    wall = time.perf_counter() - t0
+    per_slice = np.array([a + b for a, b in res])                  # seconds per slice on one busy core
+    value = cores / float(per_slice.mean())                       # all cores busy concurrently
+    sample = ("%d slices (1 per core x %d), Keff hist path in full + reference LWA j-loop on %d of %d rows "
+              "extrapolated x%.1f; mean %.2f s Keff + %.2f s LWA per slice per core; sample wall %.1f s"
+              % (n, per_core, nrows, NY, NY / float(nrows), np.mean([a for a, _ in res]),
+                 np.mean([b for _, b in res]), wall))
+    return value, cores, sample
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    vals, t_all = [], time.perf_counter()
+    for i in range(args.warmup + args.steps):
+        v, cores, sample = cpu_sample(nrows=24, per_core=1)
+        if i >= args.warmup:
+            vals.append(v)
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "slices/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * (time.perf_counter() - t_all) / max(1, args.warmup + args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "C4: Keff+LWA, 721x1440 fp32 tracer, 361 contours", "impl_note":
+                   "NumPy restatement of xcontour's hist path + LWA j-loop (reference itself is not "
+                   "importable here: no xarray/xhistogram)"},
+        "cpu_baseline": {"value": value, "unit": "slices/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.p = gpu_index, None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        load = [x for x in sm if smax and x > 0.5 * smax] or sm
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": smax,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from xcontour_b200 import ops
+    from xcontour_b200._lib import N_STAGES, STAGE_NAMES
+    from xcontour_b200.pipeline import HostStreamer, KeffLwaPlan
+    from oracle import xcontour_oracle as O       # dA construction + cpu_baseline only
+
+    torch.cuda.set_device(local_rank)
+    ops.require_cuda()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    lat, lon = grid()
+    dA = O.latlon_cell_area(lat, lon).astype(np.float32)
+    plan = KeffLwaPlan(lat, lon, dA, NLEV, increase=True, lt=True, sub_batch=args.sub_batch)
+    B = args.batch
+
+    # synthetic slices of this rank (global index = rank*B + s), generated on the device
+    phi = torch.deg2rad(torch.tensor(lat, dtype=torch.float64, device=dev))[:, None]
+    lam = torch.deg2rad(torch.tensor(lon, dtype=torch.float64, device=dev))[None, :]
+    q = torch.empty((B, NY, NX), dtype=torch.float32, device=dev)
+    for s in range(B):
+        g = torch.Generator(device=dev); g.manual_seed(1234 + rank * B + s)
+        phase = 2 * np.pi * torch.rand((), generator=g, device=dev, dtype=torch.float64)
+        noise = torch.randn((NY, NX), generator=g, device=dev, dtype=torch.float32)
+        q[s] = (torch.sin(phi) + 0.3 * torch.cos(phi) ** 2 * torch.sin(6 * lam + 3 * phi + phase)).float() + 0.02 * noise
+    out = plan.alloc_outputs(B)
+    ws = torch.empty(plan.workspace_bytes(B), dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        plan.run(q, out=out, ws=ws)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ops.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        plan.run(q, out=out, ws=ws)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ops.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * args.steps / (ms_max * 1e-3)
+
+    # per-stage device time, CUDA events on the launching stream inside the same call
+    stage = (ctypes.c_float * N_STAGES)()
+    acc = np.zeros(N_STAGES)
+    for _ in range(args.steps):
+        plan.run(q, out=out, ws=ws, stage_ms=stage)
+        acc += np.array(list(stage))
+    acc /= args.steps                                             # ms per step, per stage
+    stages = {n: float(v) for n, v in zip(STAGE_NAMES, acc)}
+
+    # end to end: pinned host slices -> H2D -> fused batch -> D2H of every result
+    eb = min(args.e2e_batch, B)
+    streamer = HostStreamer(plan, eb, copy_lwa=True)
+    q_host = torch.empty((B, NY, NX), dtype=torch.float32).pin_memory()
+    q_host.copy_(q)
+    sink = {"n": 0, "chk": 0.0}
+
+    def consume(s0, s1, host):
+        sink["n"] += s1 - s0
+        sink["chk"] += float(host["area"][:, -1].sum())           # a result actually read on the host
+
+    streamer.run(q_host, consume)                                  # warm-up
+    barrier()
+    streamer.h2d_bytes = streamer.d2h_bytes = 0
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        streamer.run(q_host, consume)
+    torch.cuda.synchronize()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / float(te.item())
+
+    if rank == 0:
+        peak, peak_src = peak_hbm()
+        dom = max(STAGE_ALG_BYTES, key=lambda k: stages[k])
+        ach = STAGE_ALG_BYTES[dom] * B / (stages[dom] * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": "slices/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "C4: Keff+LWA, 721x1440 fp32 tracer, 361 contours, increase&lt, "
+                                   "|grad q|^2 in flight, fp64 LWA out",
+                       "slices_per_step_per_gpu": B, "sub_batch": args.sub_batch or "auto",
+                       "l2": "inputs larger than L2 (%.0f MB of q + %.0f MB of LWA per step)"
+                             % (B * P * 4 / 1e6, B * P * 8 / 1e6),
+                       "parallelism": "slices sharded over %d GPU(s), no data-path collective" % world},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+                         "stage_ms_per_step": stages,
+                         "pipeline": {"alg_bytes_per_slice": ALG_BYTES_PER_SLICE,
+                                      "achieved": ALG_BYTES_PER_SLICE * value / world / 1e9,
+                                      "frac": ALG_BYTES_PER_SLICE * value / world / 1e9 / peak}},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "slices/s",
+                    "h2d_bytes_per_step": streamer.h2d_bytes // e2e_steps,
+                    "d2h_bytes_per_step": streamer.d2h_bytes // e2e_steps,
+                    "timing": "host wall clock around pinned H2D + kernels + D2H, max over ranks",
+                    "batch": eb},
+            "gpu_launches": int(launches) * world,
+        }
+        if world == 1 and not args.no_cpu:
+            v, cores, sample = cpu_sample(nrows=96, per_core=3)
+            line["cpu_baseline"] = {"value": v, "unit": "slices/s", "cores": cores, "kind": "port",
+                                    "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="slices per step per GPU")
+    ap.add_argument("--sub-batch", type=int, default=0, help="slices per internal pass (0 = auto)")
+    ap.add_argument("--e2e-batch", type=int, default=16)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -197,7 +197,9 @@ int xc_grad2_latlon(const void* q, int q_dtype, long S, int n_y, int n_x,
  *   ctr, area, intgrdS, latEq, Lmin, dintSdA, dqdA, Leq2, nkeff
  * Qref: [S][n_y] fp64;  lwa: [S][n_y][n_x] fp64.
  * grdS: [S][P] (dtype grdS_dtype) or NULL -> computed in flight from q with the
- * stencil of (7) and never written to HBM.
+ * stencil of (7) inside the binning kernel and never written to HBM.
+ * The batch is walked in passes of `sub_batch` slices so that the three reads of
+ * a slice (min/max, binning, LWA) after the first are served by the 126 MB L2.
  * ---------------------------------------------------------------------- */
 typedef struct xc_keff_lwa_args {
     const void*   q;          int q_dtype;
@@ -212,9 +214,16 @@ typedef struct xc_keff_lwa_args {
     const double* ww;         /* [n_y][n_x] from xc_lwa_weights */
     double        keff_mask;  /* cal_normalized_Keff(mask=...) */
     int           part;
+    int           sub_batch;  /* slices per internal pass; 0 = auto (one pass's q + LWA stay L2-resident) */
     double *ctr, *area, *intgrdS, *latEq, *Lmin, *dintSdA, *dqdA, *Leq2, *nkeff;
     double *Qref, *lwa;
+    /* optional HOST pointer to XC_N_STAGES floats: per-stage device time in ms
+     * (CUDA events around every stage, summed over the passes of this call).  When
+     * non-NULL the call synchronises the stream before returning.  Stages:
+     * 0 min/max+levels, 1 edges, 2 binning+scan, 3 contour-space epilogue, 4 LWA. */
+    float* stage_ms;
 } xc_keff_lwa_args;
+#define XC_N_STAGES 5
 
 size_t xc_keff_lwa_batch_workspace_bytes(long S, int n_y, int n_x, int N);
 int xc_keff_lwa_batch(const xc_keff_lwa_args* args,

@@ -1,0 +1,518 @@
+"""
+GPU parity suite (-m gpu): every entry point of the C ABI, called the way the
+product calls it (ctypes -> libxcb200.so, device buffers from torch), against
+the NumPy oracle on the same seeded inputs and on the committed fixtures.
+
+Bars (BASELINE.json north_star): contour bin assignment bit-exact given identical
+fp64 levels; levels / edges / np.interp / d/dA bit-exact; integrals and
+Keff / LWA / LAPE fields within 1e-10 (relative to the field maximum -- the
+tolerance is written next to each assertion).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from conftest import GOLDEN, synth_c4
+from oracle import xcontour_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL_INT = 1e-12      # integrals (fp64 accumulation, different summation order)
+RTOL_FIELD = 1e-10    # Keff / LWA / LAPE fields, relative to the field max
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from xcontour_b200 import ops as _ops
+    _ops.require_cuda()
+    return _ops
+
+
+def dev(ops, a):
+    return ops.to_dev(np.ascontiguousarray(a))
+
+
+def relmax(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    scale = np.nanmax(np.abs(b)) if np.isfinite(np.nanmax(np.abs(b))) and np.nanmax(np.abs(b)) > 0 else 1.0
+    return np.nanmax(np.abs(a - b)) / scale
+
+
+def same_nan(a, b):
+    return np.array_equal(np.isnan(a), np.isnan(b))
+
+
+# ---------------------------------------------------------------- (1) levels
+def test_levels_golden_notebook_on_gpu(ops):
+    g = json.load(open(os.path.join(GOLDEN, "contours_pv.json")))
+    rows = np.array([[np.float32(x) for x in r] for r in g["printed"]])
+    q = np.stack([rows[:, 0], rows[:, -1]], axis=1).astype(np.float32)       # [6, P=2]
+    lv, mm = ops.minmax_levels(dev(ops, q), g["levels_N"], True, 0)
+    got = lv.cpu().numpy().astype(np.float32)[:, g["columns"]]
+    assert np.array_equal(got, rows)
+    assert np.array_equal(mm.cpu().numpy(), q.astype(np.float64))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("increase", [True, False])
+@pytest.mark.parametrize("shape", [(5, 37, 53), (3, 64, 128), (2, 721, 1440)])
+def test_levels_bit_exact(ops, dtype, increase, shape):
+    rng = np.random.default_rng(7)
+    q = (rng.standard_normal(shape) * 3e-5 + 1e-4).astype(dtype)
+    q[0, 0, :5] = np.nan
+    q[1, -1, -1] = np.nan
+    for out_dt, code in ((np.float32, 0), (np.float64, 1)):
+        ref = O.cal_contours(q, 121, increase, out_dt)
+        lv, _ = ops.minmax_levels(dev(ops, q.reshape(shape[0], -1)), 121, increase, code)
+        assert np.array_equal(lv.cpu().numpy().astype(out_dt), ref)
+
+
+@pytest.mark.parametrize("cdt", [np.float32, np.float64])
+@pytest.mark.parametrize("time_branch", [True, False])
+def test_hist_edges_bit_exact(ops, cdt, time_branch):
+    rng = np.random.default_rng(3)
+    q = (rng.standard_normal((4, 20, 30)) * 2e-4).astype(np.float32)
+    for increase in (True, False):
+        ctr = O.cal_contours(q, 33, increase, cdt)
+        e, d = ops.hist_edges(dev(ops, ctr.astype(np.float64)), 0 if cdt == np.float32 else 1, time_branch)
+        e, d = e.cpu().numpy(), d.cpu().numpy()
+        for s in range(4):
+            ref, binc = O.hist_edges(ctr[s], time_branch)
+            nudged = np.concatenate((ref[:-1], ref[-1:] + 1e-8)).astype(ref.dtype)
+            assert np.array_equal(e[s], nudged.astype(np.float64))
+            assert d[s] == (0 if binc else 1)
+
+
+# ---------------------------------------------------------------- (2) binning
+def _edges_for(ctr, time_branch):
+    ref, binc = O.hist_edges(ctr, time_branch)
+    return np.concatenate((ref[:-1], ref[-1:] + 1e-8)).astype(ref.dtype).astype(np.float64), binc
+
+
+@pytest.mark.parametrize("qdt", [np.float32, np.float64])
+def test_bin_assignment_bit_exact(ops, vort, qdt):
+    lat, lon, q = vort
+    q = q.astype(qdt)
+    dA = O.latlon_cell_area(lat, lon).astype(np.float32)
+    q3 = np.stack([q, q[::-1], q * 0.5])
+    ctr = O.cal_contours(q3, 121, True)
+    # plant cells exactly on levels, NaN, and out-of-range values
+    q3[0, 10, :121] = ctr[0].astype(qdt)
+    q3[1, 5, :7] = np.nan
+    q3[2, 0, 0] = 1.0
+    q3[2, 0, 1] = -1.0
+    edges = np.stack([_edges_for(ctr[s], True)[0] for s in range(3)])
+    cdf, pdf, idx = ops.bin_accumulate(dev(ops, q3.reshape(3, -1)), dev(ops, edges), dev(ops, dA.reshape(-1)),
+                                       want_pdf=True, want_idx=True)
+    idx = idx.cpu().numpy()
+    for s in range(3):
+        e, _ = O.hist_edges(ctr[s], True)
+        ref = O.digitize_bins(q3[s].ravel(), e)
+        assert np.array_equal(idx[s], ref)                        # bit-exact bin assignment
+        refpdf = O.xhistogram_1d(q3[s], e, dA)
+        assert relmax(pdf[s, 0].cpu().numpy(), refpdf) <= RTOL_INT
+
+
+@pytest.mark.parametrize("increase,lt", [(True, True), (True, False), (False, True), (False, False)])
+def test_cdf_hist_path(ops, vort, increase, lt):
+    lat, lon, q = vort
+    dA = O.latlon_cell_area(lat, lon).astype(np.float32)
+    rng = np.random.default_rng(11)
+    q3 = np.stack([q, q[::-1]])
+    g = np.abs(rng.standard_normal(q3.shape)).astype(np.float32) * 1e-9
+    g[0, 3, 3] = np.nan                                           # fillna(0) on the weights
+    ctr = O.cal_contours(q3, 121, increase)
+    ref_a = O.cal_integral_within_contours_hist(q3, ctr, dA, lt)
+    ref_g = O.cal_integral_within_contours_hist(q3, ctr, dA, lt, integrand=g)
+    e, d = ops.hist_edges(dev(ops, ctr.astype(np.float64)), 0, True)
+    from xcontour_b200._lib import SCAN_PREFIX, SCAN_TOTAL_MINUS
+    cdf, _, _ = ops.bin_accumulate(dev(ops, q3.reshape(2, -1)), e, dev(ops, dA.reshape(-1)),
+                                   acc_area=True, integrands=[dev(ops, g.reshape(2, -1))],
+                                   scan_mode=SCAN_PREFIX if lt else SCAN_TOTAL_MINUS, decreasing=d)
+    cdf = cdf.cpu().numpy()
+    assert relmax(cdf[:, 0], ref_a) <= RTOL_INT
+    assert relmax(cdf[:, 1], ref_g) <= RTOL_INT
+    # run-to-run determinism (fixed reduction order, no atomics on this path)
+    cdf2, _, _ = ops.bin_accumulate(dev(ops, q3.reshape(2, -1)), e, dev(ops, dA.reshape(-1)),
+                                    acc_area=True, integrands=[dev(ops, g.reshape(2, -1))],
+                                    scan_mode=SCAN_PREFIX if lt else SCAN_TOTAL_MINUS, decreasing=d)
+    assert np.array_equal(cdf, cdf2.cpu().numpy())
+
+
+def test_cdf_many_bins_shared_copy_path(ops):
+    """N = 2048 with K = 2 does not fit 8 private copies -> shared-copy atomics."""
+    rng = np.random.default_rng(5)
+    q = rng.random((2, 128, 512)).astype(np.float32)
+    dA = (rng.random((128, 512)) + 0.5)
+    g = rng.random((2, 128, 512))
+    ctr = O.cal_contours(q, 2048, True, np.float64)
+    ref_a = O.cal_integral_within_contours_hist(q, ctr, dA, True)
+    ref_g = O.cal_integral_within_contours_hist(q, ctr, dA, True, integrand=g)
+    e, d = ops.hist_edges(dev(ops, ctr), 1, True)
+    cdf, _, _ = ops.bin_accumulate(dev(ops, q.reshape(2, -1)), e, dev(ops, dA.reshape(-1)), acc_area=True,
+                                   integrands=[dev(ops, g.reshape(2, -1))], decreasing=d)
+    cdf = cdf.cpu().numpy()
+    assert relmax(cdf[:, 0], ref_a) <= RTOL_INT and relmax(cdf[:, 1], ref_g) <= RTOL_INT
+
+
+def test_cdf_ragged_and_tiny(ops):
+    rng = np.random.default_rng(9)
+    for shape, N in (((1, 1, 3), 2), ((3, 7, 13), 5), ((2, 1, 131), 17)):
+        q = rng.standard_normal(shape).astype(np.float32)
+        dA = (rng.random(shape[1:]) + 1).astype(np.float32)
+        ctr = O.cal_contours(q, N, True)
+        ref = O.cal_integral_within_contours_hist(q, ctr, dA, True, time_branch=True)
+        e, d = ops.hist_edges(dev(ops, ctr.astype(np.float64)), 0, True)
+        cdf, _, _ = ops.bin_accumulate(dev(ops, q.reshape(shape[0], -1)), e, dev(ops, dA.reshape(-1)), decreasing=d)
+        assert relmax(cdf[:, 0].cpu().numpy(), ref) <= RTOL_INT
+
+
+# ---------------------------------------------------------------- (3)-(5) contour space
+def test_interp_bit_exact(ops):
+    rng = np.random.default_rng(2)
+    S, n, M = 6, 57, 91
+    xp = np.cumsum(rng.random((S, n)), axis=1)
+    xp[2, 10:14] = xp[2, 10]                                       # ties in the table
+    fp = rng.standard_normal((S, n))
+    x = rng.random((S, M)) * (xp[:, -1:] + 2) - 1                  # includes out-of-range
+    x[0, :n] = xp[0]                                               # exact hits
+    x[1, 0] = np.nan
+    out = ops.interp(dev(ops, x), dev(ops, xp), dev(ops, fp), reverse=0).cpu().numpy()
+    ref = np.stack([np.interp(x[s], xp[s], fp[s]) for s in range(S)])
+    assert np.array_equal(out, ref, equal_nan=True)
+    out = ops.interp(dev(ops, x), dev(ops, xp[:, ::-1].copy()), dev(ops, fp[:, ::-1].copy()), reverse=-1).cpu().numpy()
+    assert np.array_equal(out, ref, equal_nan=True)                # auto-detected decreasing tables
+    out = ops.interp(dev(ops, x[0]), dev(ops, xp), dev(ops, fp), reverse=0).cpu().numpy()
+    assert np.array_equal(out, np.stack([np.interp(x[0], xp[s], fp[s]) for s in range(S)]), equal_nan=True)
+
+
+def test_gradient_and_keff_epilogue(ops):
+    rng = np.random.default_rng(4)
+    S, N = 5, 121
+    area = np.cumsum(rng.random((S, N)) * 1e12, axis=1)
+    area[1, 40:43] = area[1, 40]                                   # empty bins -> 0/0, x/0
+    ctr = O.cal_contours(rng.standard_normal((S, 9, 9)).astype(np.float32), N, True)
+    intg = np.cumsum(rng.random((S, N)), axis=1)
+    from xcontour_b200._lib import XC_F32, XC_F64, XC_F32_AS_F64
+    with np.errstate(all="ignore"):
+        ref_dq = O.cal_gradient_wrt_area(ctr, area)
+        ref_dg = O.cal_gradient_wrt_area(intg, area)
+        ref_l2 = O.cal_sqared_equivalent_length(ref_dg, ref_dq)
+    dq = ops.gradient_wrt_area(dev(ops, ctr), XC_F32, dev(ops, area), XC_F64)
+    dq2 = ops.gradient_wrt_area(dev(ops, ctr.astype(np.float64)), XC_F32_AS_F64, dev(ops, area), XC_F64)
+    dg = ops.gradient_wrt_area(dev(ops, intg), XC_F64, dev(ops, area), XC_F64)
+    assert np.array_equal(dq.cpu().numpy(), ref_dq, equal_nan=True)
+    assert np.array_equal(dq2.cpu().numpy(), ref_dq, equal_nan=True)
+    assert np.array_equal(dg.cpu().numpy(), ref_dg, equal_nan=True)
+    l2 = ops.leq2(dg, dq).cpu().numpy()
+    assert np.array_equal(l2, ref_l2, equal_nan=True)
+    lat = rng.uniform(-90, 90, (S, N))
+    ref_lm = O.latitude_lengths_at(lat)
+    lm = ops.lmin(dev(ops, lat)).cpu().numpy()
+    assert np.allclose(lm, ref_lm, rtol=4e-16, atol=1e-9)          # cos(): <= 1 ulp between libms
+    ref_nk = O.cal_normalized_Keff(ref_l2, ref_lm)
+    nk = ops.nkeff(dev(ops, ref_l2), dev(ops, ref_lm), 1e5).cpu().numpy()
+    assert np.array_equal(nk, ref_nk, equal_nan=True)
+    a = rng.random((S, N)) * 5.1e14
+    assert np.allclose(ops.eqlat(dev(ops, a)).cpu().numpy(), O.equivalent_latitudes(a), rtol=1e-14, atol=1e-12)
+    # fp32 / fp32 quotient is rounded in fp32 like NumPy's
+    a32 = area.astype(np.float32)
+    r = ops.gradient_wrt_area(dev(ops, ctr), XC_F32, dev(ops, a32), XC_F32).cpu().numpy().astype(np.float32)
+    with np.errstate(all="ignore"):
+        assert np.array_equal(r, O.cal_gradient_wrt_area(ctr, a32), equal_nan=True)
+
+
+# ---------------------------------------------------------------- (6) LWA
+def _sorted_profile(q3, lat, dA, N, increase, lt=True):
+    ctr = O.cal_contours(q3, N, increase)
+    area = O.cal_integral_within_contours_hist(q3, ctr, dA, lt)
+    tbl, c = O.cal_area_eqCoord_table_hist(lat, np.ones_like(q3[0]), dA, 0, increase, lt)
+    latEq = O.table_lookup_coordinates(area, tbl, c)
+    return O.interp_to_coords(lat, latEq, ctr)
+
+
+@pytest.mark.parametrize("increase", [True, False])
+@pytest.mark.parametrize("part", ["all", "upper", "lower"])
+def test_lwa_vs_reference_loop(ops, vort, increase, part):
+    lat, lon, q = vort
+    dA = O.latlon_cell_area(lat, lon).astype(np.float32)
+    q3 = np.stack([q, q[::-1]])
+    Q = _sorted_profile(q3, lat, dA, 121, increase)
+    ref = O.cal_local_wave_activity(q3, Q, dA, lat, increase, part)
+    ww = ops.lwa_weights(dev(ops, dA.reshape(-1)))
+    out = ops.lwa(dev(ops, q3), dev(ops, Q), ww, increase, part, 1).cpu().numpy()
+    assert relmax(out, ref) <= RTOL_FIELD * 1e-2                    # measured ~1e-15
+    assert (out >= -1e-12 * np.abs(ref).max()).all() if increase else (out <= 1e-12 * np.abs(ref).max()).all()
+
+
+def test_lwa_unsorted_profile_nan_and_fp64(ops, vort):
+    """A profile that is not sorted (or has NaN) takes the exact O(n^2) kernel;
+    NaN tracer cells contribute nothing (skipna sum, core.py:1376)."""
+    lat, lon, q = vort
+    dA = O.latlon_cell_area(lat, lon)
+    q3 = np.stack([q[::4, ::8], q[::4, ::8][::-1]]).astype(np.float64)
+    lat4, dA4 = lat[::4], dA[::4, ::8].copy()
+    q3[0, 5:9, 3:11] = np.nan
+    Q = _sorted_profile(np.nan_to_num(q3), lat4, dA4, 41, True)
+    Q[1] = Q[1][np.random.default_rng(0).permutation(Q.shape[1])]  # scrambled -> brute force
+    Q[0, 7] = Q[0, 8]                                               # a tie stays on the fast path
+    ref = O.cal_local_wave_activity(q3, Q, dA4, lat4, True)
+    ww = ops.lwa_weights(dev(ops, dA4.reshape(-1)))
+    out = ops.lwa(dev(ops, q3), dev(ops, Q), ww, True, "all", 1).cpu().numpy()
+    assert relmax(out, ref) <= RTOL_FIELD * 1e-2
+    Q[0, 3] = np.nan
+    ref = O.cal_local_wave_activity(q3, Q, dA4, lat4, True)
+    out = ops.lwa(dev(ops, q3), dev(ops, Q), ww, True, "all", 1).cpu().numpy()
+    assert relmax(out, ref) <= RTOL_FIELD * 1e-2 and np.all(out[0, 3] == 0)
+
+
+def test_lwa_variant2_and_masks(ops, vort):
+    lat, lon, q = vort
+    dA = O.latlon_cell_area(lat, lon).astype(np.float32)
+    q3 = q[None, ::2, ::4].copy()
+    lat2, dA2 = lat[::2], dA[::2, ::4].copy()
+    for increase in (True, False):
+        Q = _sorted_profile(q3, lat2, dA2, 61, increase)
+        ww = ops.lwa_weights(dev(ops, dA2.reshape(-1)))
+        for variant in (1, 2):
+            ref, ctrs, masks = O.cal_local_wave_activity(q3, Q, dA2, lat2, increase, "all",
+                                                         mask_idx=[3, 60, 100], variant=variant)
+            out = ops.lwa(dev(ops, q3), dev(ops, Q), ww, increase, "all", variant).cpu().numpy()
+            assert relmax(out, ref) <= RTOL_FIELD * 1e-2
+            for j, m in zip([3, 60, 100], masks):
+                got = ops.lwa_mask(dev(ops, q3), dev(ops, Q), j, increase, variant).cpu().numpy()
+                assert np.array_equal(got, m)                      # integer masks bit-exact
+
+
+def test_lape_xz_plane_with_topography(ops):
+    """Config 3 stand-in (Data/internalwave.nc is missing from the mount): X-Z
+    plane, increase=False, NaN topography, time-varying contours."""
+    rng = np.random.default_rng(21)
+    nz, nx, T = 100, 448, 3
+    z = -np.arange(nz) * 2.0 - 1.0                                   # descending coordinate
+    x = np.arange(nx) * 20.0
+    b = np.empty((T, nz, nx), np.float32)
+    for t in range(T):
+        eta = 8.0 * np.sin(2 * np.pi * x / 3000.0 + t)[None, :] * np.exp(-((z[:, None] + 80) / 60.0) ** 2)
+        b[t] = (2e-4 * 9.81 * (10.0 * np.tanh((z[:, None] - eta + 100) / 40.0)) +
+                1e-5 * rng.standard_normal((nz, nx))).astype(np.float32)
+    b[:, 80:, 300:] = np.nan                                         # topography
+    dA = np.full((nz, nx), 40.0, np.float32)
+    mask = (~np.isnan(b[0])).astype(np.float32)
+    ctr = O.cal_contours(b, 121, increase=False)
+    area = O.cal_integral_within_contours_hist(b, ctr, dA, False)
+    tbl, c = O.cal_area_eqCoord_table_hist(z.astype(np.float32), mask, dA, 0, False, False)
+    zEq = O.table_lookup_coordinates(area, tbl, c)
+    Q = O.interp_to_coords(z.astype(np.float32), zEq, ctr)
+    ref = O.cal_local_wave_activity(b, Q, dA, z, False)
+    ww = ops.lwa_weights(dev(ops, dA.reshape(-1)))
+    out = ops.lwa(dev(ops, b), dev(ops, Q), ww, False, "all", 1).cpu().numpy()
+    assert relmax(out, ref) <= RTOL_FIELD * 1e-2
+    assert (out <= 0).all()                                          # LAPE is plotted as -lape >= 0
+
+
+# ---------------------------------------------------------------- (7) stencil
+def test_grad2_latlon(ops):
+    lat, lon, q = synth_c4(2, 91, 180)
+    ref = O.squared_gradient_latlon(q, lat, lon)
+    lat_rad = np.deg2rad(lat.astype(np.float64))
+    lam = np.deg2rad(lon.astype(np.float64))
+    out = ops.grad2_latlon(dev(ops, q), dev(ops, lat_rad), float(lam[1] - lam[0])).cpu().numpy()
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(out), fin)
+    assert np.allclose(out[fin], ref[fin], rtol=1e-13, atol=0)       # cos() ulp at the rows only
+
+
+# ---------------------------------------------------------------- Contour2D API, reference call order
+def _oracle_keff_chain(q3, lat, lon, dA, grdS, N, increase, lt):
+    ctr = O.cal_contours(q3, N, increase)
+    tbl, c = O.cal_area_eqCoord_table_hist(lat, np.ones_like(q3[0]), dA, 0, increase, lt)
+    per = q3.shape[0] > 1
+    cc = ctr if per else ctr[0]
+    area = O.cal_integral_within_contours_hist(q3, cc, dA, lt)
+    intg = O.cal_integral_within_contours_hist(q3, cc, dA, lt, integrand=grdS)
+    latEq = O.table_lookup_coordinates(area, tbl, c)
+    with np.errstate(all="ignore"):
+        Lmin = O.latitude_lengths_at(latEq)
+        dintSdA = O.cal_gradient_wrt_area(intg, area)
+        dqdA = O.cal_gradient_wrt_area(ctr, area)
+        Leq2 = O.cal_sqared_equivalent_length(dintSdA, dqdA)
+        nkeff = O.cal_normalized_Keff(Leq2, Lmin)
+    return dict(ctr=ctr, table=tbl, area=area, intgrdS=intg, latEq=latEq, Lmin=Lmin,
+                dintSdA=dintSdA, dqdA=dqdA, Leq2=Leq2, nkeff=nkeff)
+
+
+def _close(a, b, rtol):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    assert np.array_equal(np.isinf(a), np.isinf(b))
+    f = np.isfinite(b)
+    assert np.allclose(a[f], b[f], rtol=rtol, atol=0), np.abs(a[f] - b[f]).max()
+
+
+@pytest.mark.parametrize("increase,lt", [(True, True), (True, False), (False, True), (False, False)])
+def test_contour2d_keff_lwa_workflow(ops, vort, increase, lt):
+    """tests/test_Keff_atmos.py:76-92 and tests/test_LWA.py:57-77 call order on
+    Data/barotropic_vorticity.nc through the drop-in classes."""
+    import xcontour_b200 as xb
+    lat, lon, q = vort
+    dA = O.latlon_cell_area(lat, lon).astype(np.float32)
+    grd = O.squared_gradient_latlon(q, lat, lon).astype(np.float32)
+    coords = {"latitude": lat, "longitude": lon}
+    tracer = xb.DataArray(q, dims=("latitude", "longitude"), coords=coords, name="absolute_vorticity")
+    grdS = xb.DataArray(grd, dims=("latitude", "longitude"), coords=coords, name="grdS")
+    dAx = xb.DataArray(dA, dims=("latitude", "longitude"), coords=coords)
+    mask = xb.DataArray(np.ones_like(q), dims=("latitude", "longitude"), coords=coords)
+    N = 121
+    an = xb.Contour2D(tracer, dAx, dims={"X": "longitude", "Y": "latitude"}, dimEq={"Y": "latitude"},
+                      increase=increase, lt=lt)
+    ctr = an.cal_contours(N)
+    table = an.cal_area_eqCoord_table_hist(mask)
+    area = an.cal_integral_within_contours_hist(ctr).rename("intArea")
+    intgrdS = an.cal_integral_within_contours_hist(ctr, integrand=grdS).rename("intgrdS")
+    latEq = table.lookup_coordinates(area).rename("latEq")
+    Lmin = xb.latitude_lengths_at(latEq).rename("Lmin")
+    dintSdA = an.cal_gradient_wrt_area(intgrdS, area).rename("dintSdA")
+    dqdA = an.cal_gradient_wrt_area(ctr, area)
+    assert dqdA.name == "dabsolute_vorticitydA"                                   # core.py:488
+    dqdA = dqdA.rename("dqdA")
+    Leq2 = an.cal_sqared_equivalent_length(dintSdA, dqdA)
+    nkeff = an.cal_normalized_Keff(Leq2, Lmin)
+    ref = _oracle_keff_chain(q[None], lat, lon, dA, grd[None], N, increase, lt)
+
+    assert ctr.dims == ("contour",) and ctr.name == "absolute_vorticity" and ctr.dtype == np.float32
+    assert np.array_equal(ctr["contour"].values, np.arange(N, dtype=np.float32))
+    assert np.array_equal(ctr.values, ref["ctr"][0])                              # bit-exact levels
+    assert relmax(table._table.values, ref["table"]) <= RTOL_INT
+    assert relmax(area.values, ref["area"][0]) <= RTOL_INT
+    assert relmax(intgrdS.values, ref["intgrdS"][0]) <= RTOL_INT
+    _close(latEq.values, ref["latEq"][0], 1e-11)
+    _close(Lmin.values, ref["Lmin"][0], 1e-9)
+    _close(dqdA.values, ref["dqdA"][0], 1e-10)
+    _close(dintSdA.values, ref["dintSdA"][0], 1e-10)
+    _close(Leq2.values, ref["Leq2"][0], 1e-9)
+    assert nkeff.name == "nkeff" and Leq2.name == "Leq2"
+    _close(nkeff.values, ref["nkeff"][0], 1e-8)
+
+    ds_contour = xb.merge([ctr, area, latEq])
+    preLats = tracer["latitude"].astype(np.float32)          # tests/test_LWA.py:72
+    ds_latEq = an.interp_to_dataset(preLats, latEq, ds_contour)
+    Q = ds_latEq.absolute_vorticity
+    assert Q.dims == ("latitude",)
+    refQ = O.interp_to_coords(preLats.values, ref["latEq"], ref["ctr"])
+    _close(Q.values, refQ[0], 1e-11)
+    lwa, ctrs, masks = an.cal_local_wave_activity(tracer, Q, mask_idx=[37, 125, 170, 213], part="all")
+    refL, rc, rm = O.cal_local_wave_activity(q[None], Q.values[None], dA, lat, increase, "all",
+                                             mask_idx=[37, 125, 170, 213])
+    assert lwa.name == "LWA" and lwa.dims == tracer.dims
+    assert relmax(lwa.values, refL[0]) <= RTOL_FIELD * 1e-2
+    for m, r in zip(masks, rm):
+        assert np.array_equal(m.values, r[0])
+    lape = an.cal_local_APE(tracer, Q)
+    assert lape.name == "LAPE" and np.array_equal(lape.values, lwa.values)
+    with pytest.raises(Exception, match="invalid part"):
+        an.cal_local_wave_activity(tracer, Q, part="middle")
+    with pytest.raises(Exception, match="out of boundary"):
+        an.cal_local_wave_activity(tracer, Q, mask_idx=[256])
+
+
+def test_contour2d_strict_path_and_tables(ops, vort):
+    """cal_integral_within_contours / cal_area_eqCoord_table (core.py:73-147,
+    363-409) against the oracle's literal broadcast, incl. a land mask and a
+    level-varying (3-D) tracer -- the case the reference says xhistogram cannot do
+    (notebooks/1.Keff_atmos.ipynb cell 4)."""
+    import xcontour_b200 as xb
+    lat, lon, q = vort
+    q = q[::2, ::2].copy(); lat = lat[::2].copy(); lon = lon[::2].copy()
+    dA = O.latlon_cell_area(lat, lon)
+    q3 = np.stack([q, 0.7 * q[::-1] + 1e-5])
+    coords = {"level": np.array([300, 350]), "latitude": lat, "longitude": lon}
+    tracer = xb.DataArray(q3, dims=("level", "latitude", "longitude"), coords=coords, name="pv")
+    dAx = xb.DataArray(dA, dims=("latitude", "longitude"))
+    m = np.ones_like(q); m[40:60, 100:140] = 0
+    mask = xb.DataArray(m, dims=("latitude", "longitude"), coords={"latitude": lat, "longitude": lon})
+    for increase, lt in ((True, True), (True, False), (False, False)):
+        an = xb.Contour2D(tracer, dAx, dims={"X": "longitude", "Y": "latitude"}, dimEq={"Y": "latitude"},
+                          increase=increase, lt=lt)
+        ctr = an.cal_contours(61)
+        assert ctr.dims == ("level", "contour")
+        area = an.cal_integral_within_contours(ctr)
+        ref = O.cal_integral_within_contours(q3, ctr.values, dA, lt)
+        assert relmax(area.values, ref) <= RTOL_INT
+        areah = an.cal_integral_within_contours_hist(ctr)
+        refh = O.cal_integral_within_contours_hist(q3, ctr.values, dA, lt)
+        assert relmax(areah.values, refh) <= RTOL_INT
+        t1 = an.cal_area_eqCoord_table(mask)
+        r1, _ = O.cal_area_eqCoord_table(lat, m, dA, 0, increase, lt)
+        assert relmax(t1._table.values, r1) <= RTOL_INT
+        t2 = an.cal_area_eqCoord_table_hist(mask)
+        r2, _ = O.cal_area_eqCoord_table_hist(lat, m, dA, 0, increase, lt)
+        assert relmax(t2._table.values, r2) <= RTOL_INT
+        y = t2.lookup_coordinates(areah)
+        assert y.dims == ("level", "contour")
+        _close(y.values, O.table_lookup_coordinates(refh, r2, lat), 1e-11)
+
+
+# ---------------------------------------------------------------- (8) fused batch
+@pytest.mark.parametrize("increase,lt", [(True, True), (False, False)])
+def test_fused_batch_matches_oracle_chain(ops, increase, lt):
+    from xcontour_b200.pipeline import KeffLwaPlan
+    lat, lon, q = synth_c4(3, 91, 180)
+    dA = O.latlon_cell_area(lat, lon).astype(np.float32)
+    N = 41
+    plan = KeffLwaPlan(lat, lon, dA, N, increase=increase, lt=lt)
+    out = plan.run(dev(ops, q))
+    torch.cuda.synchronize()
+    grd = O.squared_gradient_latlon(q, lat, lon)                     # fp64, never rounded to fp32
+    ref = _oracle_keff_chain(q, lat, lon, dA, grd, N, increase, lt)
+    assert np.array_equal(out["ctr"].cpu().numpy().astype(np.float32), ref["ctr"])
+    assert relmax(out["area"].cpu().numpy(), ref["area"]) <= RTOL_INT
+    assert relmax(out["intgrdS"].cpu().numpy(), ref["intgrdS"]) <= 1e-11
+    _close(out["latEq"].cpu().numpy(), ref["latEq"], 1e-11)
+    _close(out["dqdA"].cpu().numpy(), ref["dqdA"], 1e-10)
+    _close(out["dintSdA"].cpu().numpy(), ref["dintSdA"], 1e-9)
+    _close(out["nkeff"].cpu().numpy(), ref["nkeff"], 1e-8)
+    Qref = O.interp_to_coords(lat.astype(np.float32), ref["latEq"], ref["ctr"])
+    _close(out["Qref"].cpu().numpy(), Qref, 1e-11)
+    refL = O.cal_local_wave_activity(q, out["Qref"].cpu().numpy(), dA, lat, increase)
+    assert relmax(out["lwa"].cpu().numpy(), refL) <= RTOL_FIELD * 1e-2
+
+
+def test_full_size_properties(ops):
+    """BASELINE config 4 shape (721x1440, N=361): size-independent properties."""
+    from xcontour_b200.pipeline import KeffLwaPlan
+    lat, lon, q = synth_c4(2)
+    dA = O.latlon_cell_area(lat, lon).astype(np.float32)
+    plan = KeffLwaPlan(lat, lon, dA, 361, increase=True, lt=True)
+    qd = dev(ops, q)
+    out = plan.run(qd)
+    torch.cuda.synchronize()
+    area = out["area"].cpu().numpy()
+    tot = dA.astype(np.float64).sum()
+    assert np.all(np.diff(area, axis=1) >= 0)                        # CDF monotone
+    assert np.all(np.abs(area[:, -1] - tot) / tot < 1e-6)            # area[-1] = sum dA (core.py:133-140)
+    Q = out["Qref"].cpu().numpy()
+    assert np.all(np.diff(Q, axis=1) >= 0)                           # sorted profile
+    lwa = out["lwa"].cpu().numpy()
+    assert lwa.min() >= -1e-10 * lwa.max()                           # LWA >= 0 for part='all'
+    # spot-check 5 reference rows of slice 0 against the reference's own j-loop
+    rows = [0, 100, 360, 600, 720]
+    ref = O.cal_local_wave_activity(q[:1], Q[:1], dA, lat, True, rows=rows)
+    for j in rows:
+        assert np.abs(lwa[0, j] - ref[0, j]).max() <= RTOL_FIELD * lwa.max()
+    # bit-exact bins at full size on one slice
+    ctr = out["ctr"].cpu().numpy().astype(np.float32)
+    e, _ = O.hist_edges(ctr[0], True)
+    ee, dd = ops.hist_edges(out["ctr"][:1].contiguous(), 0, True)
+    _, _, idx = ops.bin_accumulate(qd[:1].reshape(1, -1), ee, dev(ops, dA.reshape(-1)), decreasing=dd, want_idx=True)
+    assert np.array_equal(idx.cpu().numpy()[0], O.digitize_bins(q[0].ravel(), e))
+    # determinism
+    out2 = plan.run(qd, out=plan.alloc_outputs(2))
+    torch.cuda.synchronize()
+    assert torch.equal(out2["lwa"], out["lwa"]) and torch.equal(out2["nkeff"].nan_to_num(), out["nkeff"].nan_to_num())

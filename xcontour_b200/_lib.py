@@ -17,6 +17,8 @@ XC_F32, XC_F64, XC_F32_AS_F64 = 0, 1, 2
 SCAN_PREFIX, SCAN_TOTAL_MINUS, SCAN_SUFFIX = 0, 1, 2
 PART = {"all": 0, "upper": 1, "lower": 2}
 MAX_INTEGRANDS = 3
+N_STAGES = 5
+STAGE_NAMES = ("minmax_levels", "edges", "bin_accumulate", "epilogue", "lwa")
 
 
 class KeffLwaArgs(Structure):
@@ -33,11 +35,12 @@ class KeffLwaArgs(Structure):
         ("eq_coord", c_void_p),
         ("ww", c_void_p),
         ("keff_mask", c_double),
-        ("part", c_int),
+        ("part", c_int), ("sub_batch", c_int),
         ("ctr", c_void_p), ("area", c_void_p), ("intgrdS", c_void_p),
         ("latEq", c_void_p), ("Lmin", c_void_p), ("dintSdA", c_void_p),
         ("dqdA", c_void_p), ("Leq2", c_void_p), ("nkeff", c_void_p),
         ("Qref", c_void_p), ("lwa", c_void_p),
+        ("stage_ms", c_void_p),
     ]
 
 

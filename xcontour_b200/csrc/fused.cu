@@ -2,30 +2,52 @@
 // no host round-trips.  Every stage is one of the kernels the stand-alone ABI
 // entries launch (same arithmetic, same parity); the intermediate contour-space
 // arrays live in the caller's workspace.  This is the call bench.py times.
+//
+// The batch is walked in passes of `sub` slices.  A slice is read three times
+// (min/max, binning + in-flight |grad q|^2, LWA); with a pass footprint of
+// sub * (q + LWA) well inside the 126 MB L2 only the first read and the LWA
+// store touch HBM, which is the algorithmic traffic of DESIGN.md.
 #include "common.cuh"
 #include "internal.h"
+#include <stdlib.h>
+#include <vector>
 
 using namespace xc;
 
 namespace {
 struct FusedPlan {
+    long sub;
     size_t ws_minmax, ws_hist, ws_lwa;
     size_t total;
 };
-FusedPlan fused_plan(long S, int ny, int nx, int N, bool need_grd)
+
+long auto_sub_batch(long S, long P)
+{
+    const char* env = getenv("XCB200_SUB_BATCH");
+    long sub = env ? atol(env) : 0;
+    if (sub <= 0) {
+        // q (<= 8 B/cell) + LWA (8 B/cell) per slice; keep a pass under ~40 MB
+        sub = (long)(40.0e6 / (double)(P * 12));
+        if (sub < 1) sub = 1;
+    }
+    return sub < S ? sub : S;
+}
+
+FusedPlan fused_plan(long S, int ny, int nx, int N, long sub_req)
 {
     FusedPlan p;
     const long P = (long)ny * nx;
-    p.ws_minmax = xc_minmax_levels_workspace_bytes(S, P);
-    p.ws_hist = xc_bin_accumulate_workspace_bytes(S, P, N, 2);
-    p.ws_lwa = xc_lwa_workspace_bytes(S);
+    p.sub = sub_req > 0 ? (sub_req < S ? sub_req : S) : auto_sub_batch(S, P);
+    p.ws_minmax = xc_minmax_levels_workspace_bytes(p.sub, P);
+    p.ws_hist = xc_bin_accumulate_workspace_bytes(p.sub, P, N, 2);
+    p.ws_lwa = xc_lwa_workspace_bytes(p.sub);
     size_t t = 0;
     t += align_up(p.ws_minmax, 256) + align_up(p.ws_hist, 256) + align_up(p.ws_lwa, 256);
-    t += align_up((size_t)S * (N + 1) * 8, 256);            // edges
-    t += align_up((size_t)S * 4, 256);                      // decreasing
-    t += 10 * align_up((size_t)S * N * 8, 256);             // contour-space temporaries
-    t += align_up((size_t)S * ny * 8, 256);                 // Qref
-    if (need_grd) t += align_up((size_t)S * P * 8, 256);    // |grad q|^2 (fp64)
+    t += align_up((size_t)p.sub * (N + 1) * 8, 256);        // edges
+    t += align_up((size_t)p.sub * 4, 256);                  // decreasing
+    t += 9 * align_up((size_t)p.sub * N * 8, 256);          // contour-space temporaries
+    t += align_up((size_t)p.sub * ny * 8, 256);             // Qref
+    t += 2 * align_up((size_t)ny * 8, 256);                 // row metrics
     p.total = t + 4096;
     return p;
 }
@@ -34,7 +56,10 @@ FusedPlan fused_plan(long S, int ny, int nx, int N, bool need_grd)
 extern "C" size_t xc_keff_lwa_batch_workspace_bytes(long S, int n_y, int n_x, int N)
 {
     if (S <= 0 || n_y <= 0 || n_x <= 0 || N <= 0) return 0;
-    return fused_plan(S, n_y, n_x, N, true).total;
+    // sized for the largest pass any sub_batch setting can ask for
+    size_t a = fused_plan(S, n_y, n_x, N, 0).total;
+    size_t b = fused_plan(S, n_y, n_x, N, S).total;
+    return a > b ? a : b;
 }
 
 extern "C" int xc_keff_lwa_batch(const xc_keff_lwa_args* a, void* workspace, size_t ws_bytes, void* stream)
@@ -45,57 +70,101 @@ extern "C" int xc_keff_lwa_batch(const xc_keff_lwa_args* a, void* workspace, siz
     XC_REQUIRE(a->S > 0 && a->n_y >= 2 && a->n_x >= 2 && a->N >= 2 && a->n_table >= 1,
                "xc_keff_lwa_batch: bad sizes");
     XC_REQUIRE(a->grdS || a->lat_rad, "xc_keff_lwa_batch: need grdS or lat_rad for the stencil");
+    XC_REQUIRE(a->q_dtype == XC_F32 || a->q_dtype == XC_F64, "xc_keff_lwa_batch: bad q dtype");
     const long S = a->S; const int ny = a->n_y, nx = a->n_x, N = a->N;
     const long P = (long)ny * nx;
-    const bool need_grd = a->grdS == nullptr;
-    FusedPlan pl = fused_plan(S, ny, nx, N, need_grd);
+    const bool stencil = a->grdS == nullptr;
+    FusedPlan pl = fused_plan(S, ny, nx, N, a->sub_batch);
     XC_REQUIRE(workspace && ws_bytes >= pl.total, "xc_keff_lwa_batch: workspace too small (%zu < %zu)",
                ws_bytes, pl.total);
     Arena ar(workspace, ws_bytes);
     char* w_minmax = ar.take<char>(pl.ws_minmax);
     char* w_hist = ar.take<char>(pl.ws_hist);
     char* w_lwa = ar.take<char>(pl.ws_lwa);
-    double* edges = ar.take<double>((size_t)S * (N + 1));
-    int32_t* decr = ar.take<int32_t>((size_t)S);
-    auto tmp = [&](double* user) { double* t = ar.take<double>((size_t)S * N); return user ? user : t; };
-    double* ctr = tmp(a->ctr);       double* area = tmp(a->area);   double* intg = tmp(a->intgrdS);
-    double* latEq = tmp(a->latEq);   double* Lmin = tmp(a->Lmin);   double* dintSdA = tmp(a->dintSdA);
-    double* dqdA = tmp(a->dqdA);     double* Leq2 = tmp(a->Leq2);   double* nkeff = tmp(a->nkeff);
-    double* Qref = ar.take<double>((size_t)S * ny);
-    if (a->Qref) Qref = a->Qref;
-    double* grd = need_grd ? ar.take<double>((size_t)S * P) : nullptr;
+    double* edges = ar.take<double>((size_t)pl.sub * (N + 1));
+    int32_t* decr = ar.take<int32_t>((size_t)pl.sub);
+    double* t_ctr = ar.take<double>((size_t)pl.sub * N);     double* t_area = ar.take<double>((size_t)pl.sub * N);
+    double* t_intg = ar.take<double>((size_t)pl.sub * N);    double* t_latEq = ar.take<double>((size_t)pl.sub * N);
+    double* t_Lmin = ar.take<double>((size_t)pl.sub * N);    double* t_dint = ar.take<double>((size_t)pl.sub * N);
+    double* t_dq = ar.take<double>((size_t)pl.sub * N);      double* t_Leq2 = ar.take<double>((size_t)pl.sub * N);
+    double* t_nk = ar.take<double>((size_t)pl.sub * N);
+    double* t_Q = ar.take<double>((size_t)pl.sub * ny);
+    double* rcos = ar.take<double>((size_t)ny);
+    double* dphi = ar.take<double>((size_t)ny);
     XC_REQUIRE(ar.ok(), "xc_keff_lwa_batch: workspace accounting error");
 
-    // (1) levels, (1b) edges -- per-slice contours take the per-'time' branch
-    if (xc_minmax_levels(a->q, a->q_dtype, S, P, N, a->increase, a->ctr_dtype, ctr, nullptr,
-                         w_minmax, pl.ws_minmax, stream)) return 1;
-    if (xc_hist_edges(ctr, S, N, a->ctr_dtype, 1, edges, decr, stream)) return 1;
-    // (7) integrand
-    const void* integ = a->grdS; int integ_dtype = a->grdS_dtype;
-    if (need_grd) {
-        if (xc_grad2_latlon(a->q, a->q_dtype, S, ny, nx, a->lat_rad, a->dlambda, grd, XC_F64, stream)) return 1;
-        integ = grd; integ_dtype = XC_F64;
+    StencilArgs sa; sa.ny = ny; sa.nx = nx; sa.rcos = rcos; sa.dphi = dphi; sa.dlambda = a->dlambda;
+    if (stencil) { if (row_metrics(a->lat_rad, ny, rcos, dphi, stream)) return 1; }
+    // optional per-stage timing
+    cudaStream_t st = (cudaStream_t)stream;
+    const long npass = (S + pl.sub - 1) / pl.sub;
+    std::vector<cudaEvent_t> ev;
+    if (a->stage_ms) {
+        ev.resize((size_t)npass * (XC_N_STAGES + 1));
+        for (auto& e : ev) XC_CUDA_OK(cudaEventCreate(&e));
     }
-    // (2) area and int |grad q|^2 dA in one pass over q
-    ScanOut so; so.p[0] = area; so.p[1] = intg; so.p[2] = so.p[3] = nullptr; so.stride = N;
-    const void* integs[1] = { integ };
-    if (bin_accumulate_impl(a->q, a->q_dtype, S, P, edges, N + 1, N, 0, a->dA, a->dA_dtype, 1,
-                            integs, &integ_dtype, 1, nullptr,
-                            a->lt ? XC_SCAN_PREFIX : XC_SCAN_TOTAL_MINUS, decr,
-                            nullptr, so, nullptr, w_hist, pl.ws_hist, stream)) return 1;
-    // (3) latEq = Table.lookup_coordinates(area)
-    if (xc_interp(area, N, N, a->table, 0, a->table_coord, 0, a->n_table, -1, S, latEq, stream)) return 1;
-    // (5)/(4) Lmin, d/dA, Leq2, nkeff
-    if (xc_lmin(latEq, S * (long)N, Lmin, stream)) return 1;
-    if (xc_gradient_wrt_area(intg, XC_F64, area, XC_F64, S, N, dintSdA, stream)) return 1;
-    if (xc_gradient_wrt_area(ctr, a->ctr_dtype == XC_F32 ? XC_F32_AS_F64 : XC_F64, area, XC_F64, S, N, dqdA, stream)) return 1;
-    if (xc_leq2(dintSdA, dqdA, S * (long)N, Leq2, stream)) return 1;
-    if (xc_nkeff(Leq2, Lmin, a->keff_mask, S * (long)N, nkeff, stream)) return 1;
-    // (3) Q(eq_coord) = interp_to_coords(eq_coord, latEq, ctr)
-    if (xc_interp(a->eq_coord, 0, ny, latEq, N, ctr, N, N, -1, S, Qref, stream)) return 1;
-    // (6) LWA
-    if (a->lwa)
-        if (xc_lwa(a->q, a->q_dtype, S, ny, nx, Qref, a->ww, a->increase, a->part, 1, a->lwa,
-                   w_lwa, pl.ws_lwa, stream)) return 1;
+    long pass = 0;
+    auto mark = [&](int k) { if (a->stage_ms) cudaEventRecord(ev[(size_t)pass * (XC_N_STAGES + 1) + k], st); };
+    const size_t qsz = a->q_dtype == XC_F32 ? 4 : 8;
+    const size_t gsz = a->grdS_dtype == XC_F32 ? 4 : 8;
+
+    for (long s0 = 0; s0 < S; s0 += pl.sub) {
+        const long ns = S - s0 < pl.sub ? S - s0 : pl.sub;
+        auto at = [&](double* user, double* tmp) { return user ? user + s0 * (long)N : tmp; };
+        const void* q = (const char*)a->q + (size_t)s0 * P * qsz;
+        double* ctr = at(a->ctr, t_ctr);       double* area = at(a->area, t_area);
+        double* intg = at(a->intgrdS, t_intg); double* latEq = at(a->latEq, t_latEq);
+        double* Lmin = at(a->Lmin, t_Lmin);    double* dint = at(a->dintSdA, t_dint);
+        double* dq = at(a->dqdA, t_dq);        double* Leq2 = at(a->Leq2, t_Leq2);
+        double* nk = at(a->nkeff, t_nk);
+        double* Qref = a->Qref ? a->Qref + s0 * (long)ny : t_Q;
+
+        mark(0);
+        // (1) levels, (1b) edges -- per-slice contours take the per-'time' branch
+        if (xc_minmax_levels(q, a->q_dtype, ns, P, N, a->increase, a->ctr_dtype, ctr, nullptr,
+                             w_minmax, pl.ws_minmax, stream)) return 1;
+        mark(1);
+        if (xc_hist_edges(ctr, ns, N, a->ctr_dtype, 1, edges, decr, stream)) return 1;
+        mark(2);
+        // (2) area and int |grad q|^2 dA in one pass over q
+        ScanOut so; so.p[0] = area; so.p[1] = intg; so.p[2] = so.p[3] = nullptr; so.stride = N;
+        const void* integs[1] = { stencil ? nullptr : (const void*)((const char*)a->grdS + (size_t)s0 * P * gsz) };
+        const int integ_dt[1] = { a->grdS_dtype };
+        if (bin_accumulate_impl(q, a->q_dtype, ns, P, edges, N + 1, N, 0, a->dA, a->dA_dtype, 1,
+                                integs, integ_dt, stencil ? 0 : 1, nullptr,
+                                a->lt ? XC_SCAN_PREFIX : XC_SCAN_TOTAL_MINUS, decr,
+                                nullptr, so, nullptr, w_hist, pl.ws_hist, stream,
+                                stencil ? &sa : nullptr)) return 1;
+        mark(3);
+        // (3) latEq = Table.lookup_coordinates(area)
+        if (xc_interp(area, N, N, a->table, 0, a->table_coord, 0, a->n_table, -1, ns, latEq, stream)) return 1;
+        // (5)/(4) Lmin, d/dA, Leq2, nkeff
+        if (xc_lmin(latEq, ns * (long)N, Lmin, stream)) return 1;
+        if (xc_gradient_wrt_area(intg, XC_F64, area, XC_F64, ns, N, dint, stream)) return 1;
+        if (xc_gradient_wrt_area(ctr, a->ctr_dtype == XC_F32 ? XC_F32_AS_F64 : XC_F64, area, XC_F64,
+                                 ns, N, dq, stream)) return 1;
+        if (xc_leq2(dint, dq, ns * (long)N, Leq2, stream)) return 1;
+        if (xc_nkeff(Leq2, Lmin, a->keff_mask, ns * (long)N, nk, stream)) return 1;
+        // (3) Q(eq_coord) = interp_to_coords(eq_coord, latEq, ctr)
+        if (xc_interp(a->eq_coord, 0, ny, latEq, N, ctr, N, N, -1, ns, Qref, stream)) return 1;
+        mark(4);
+        // (6) LWA
+        if (a->lwa)
+            if (xc_lwa(q, a->q_dtype, ns, ny, nx, Qref, a->ww, a->increase, a->part, 1,
+                       a->lwa + (size_t)s0 * P, w_lwa, pl.ws_lwa, stream)) return 1;
+        mark(5);
+        ++pass;
+    }
+    if (a->stage_ms) {
+        XC_CUDA_OK(cudaStreamSynchronize(st));
+        for (int k = 0; k < XC_N_STAGES; ++k) a->stage_ms[k] = 0.f;
+        for (long p = 0; p < npass; ++p)
+            for (int k = 0; k < XC_N_STAGES; ++k) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, ev[(size_t)p * (XC_N_STAGES + 1) + k], ev[(size_t)p * (XC_N_STAGES + 1) + k + 1]);
+                a->stage_ms[k] += ms;
+            }
+        for (auto& e : ev) cudaEventDestroy(e);
+    }
     return 0;
 }

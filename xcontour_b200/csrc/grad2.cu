@@ -7,6 +7,7 @@
 // is fetched once per slice), the result is written with coalesced stores.
 #include "common.cuh"
 #include "grad2.cuh"
+#include "internal.h"
 
 namespace xc {
 
@@ -44,6 +45,13 @@ k_grad2(const QT* __restrict__ q, int ny, int nx, const double* __restrict__ lat
 }  // namespace xc
 
 using namespace xc;
+
+int xc::row_metrics(const double* lat_rad, int ny, double* rcos, double* dphi, void* stream)
+{
+    k_row_metrics<<<(ny + 255) / 256, 256, 0, (cudaStream_t)stream>>>(lat_rad, ny, rcos, dphi);
+    XC_LAUNCH_OK();
+    return 0;
+}
 
 extern "C" int xc_grad2_latlon(const void* q, int q_dtype, long S, int n_y, int n_x,
                                const double* lat_rad, double dlambda,

@@ -15,6 +15,7 @@
 // this round and does a plain 128-bit read-modify-write, the rest retry.
 #include "common.cuh"
 #include "internal.h"
+#include "grad2.cuh"
 #include <math_constants.h>
 
 namespace xc {
@@ -27,6 +28,8 @@ struct HistParams {
     const void* dA; int dA_f32; int acc_area;
     const void* integ[XC_MAX_INTEGRANDS]; int integ_f32[XC_MAX_INTEGRANDS]; int n_int;
     const uint8_t* q_mask;
+    // in-flight |grad q|^2 integrand (last accumulator slot) -- see grad2.cuh
+    int stencil; int ny, nx; const double* rcos; const double* dphi; double two_dlam;
     double* part;            // [S][C][K][N]
     int32_t* bin_idx;        // [S][P] or null
     int ncopy;
@@ -203,6 +206,13 @@ k_hist(const HistParams p)
                         w[k++] = isnan(pr) ? 0.0 : pr;             // fillna(0), core.py:449
                     }
                 }
+                if (p.stencil && k < K) {
+                    const int j = (int)(i / p.nx), col = (int)(i - (long)j * p.nx);
+                    const double gq = grad2_cell(qs, j, col, p.ny, p.nx, __ldg(p.rcos + j),
+                                                 __ldg(p.dphi + j), p.two_dlam);
+                    const double pr = __dmul_rn(gq, ad);
+                    w[k++] = isnan(pr) ? 0.0 : pr;
+                }
             }
             if (PRIVATE) scatter_private<K>(Hw, tagw, bins[u], w, act, lane);
             else         scatter_atomic<K>(Hw, bins[u], w, act);
@@ -354,15 +364,17 @@ int xc::bin_accumulate_impl(const void* q, int q_dtype, long S, long P,
                             int n_int, const uint8_t* q_mask,
                             int scan_mode, const int32_t* decreasing,
                             double* pdf, const ScanOut& so, int32_t* bin_idx,
-                            void* workspace, size_t ws_bytes, void* stream)
+                            void* workspace, size_t ws_bytes, void* stream,
+                            const StencilArgs* stencil)
 {
     XC_REQUIRE(q && edges && dA, "xc_bin_accumulate: null pointer");
     XC_REQUIRE(S > 0 && P > 0 && N >= 1, "xc_bin_accumulate: need S>0, P>0, N>=1");
     XC_REQUIRE(q_dtype == XC_F32 || q_dtype == XC_F64, "xc_bin_accumulate: bad q dtype");
     XC_REQUIRE(n_int >= 0 && n_int <= XC_MAX_INTEGRANDS, "xc_bin_accumulate: n_int out of range");
     XC_REQUIRE(edges_stride == 0 || edges_stride == N + 1, "xc_bin_accumulate: edges_stride must be 0 or N+1");
-    const int K = (acc_area ? 1 : 0) + n_int;
+    const int K = (acc_area ? 1 : 0) + n_int + (stencil ? 1 : 0);
     XC_REQUIRE(K >= 1 && K <= 4, "xc_bin_accumulate: nothing to accumulate");
+    XC_REQUIRE(!stencil || (long)stencil->ny * stencil->nx == P, "xc_bin_accumulate: stencil shape");
     HistPlan pl = plan_hist(S, P, N, K);
     XC_REQUIRE(pl.ncopy >= 1, "xc_bin_accumulate: N=%d with K=%d does not fit shared memory", N, K);
     XC_REQUIRE(workspace && ws_bytes >= xc_bin_accumulate_workspace_bytes(S, P, N, K),
@@ -380,6 +392,11 @@ int xc::bin_accumulate_impl(const void* q, int q_dtype, long S, long P,
         XC_REQUIRE(n >= n_int || hp.integ[n], "xc_bin_accumulate: null integrand");
     }
     hp.q_mask = q_mask;
+    hp.stencil = stencil ? 1 : 0;
+    if (stencil) {
+        hp.ny = stencil->ny; hp.nx = stencil->nx; hp.rcos = stencil->rcos; hp.dphi = stencil->dphi;
+        hp.two_dlam = 2.0 * stencil->dlambda;
+    } else { hp.ny = hp.nx = 0; hp.rcos = hp.dphi = nullptr; hp.two_dlam = 0.0; }
     hp.part = ar.take<double>((size_t)S * pl.C * K * N);
     hp.bin_idx = bin_idx;
     hp.ncopy = pl.ncopy;

@@ -9,6 +9,11 @@ namespace xc {
 // where the scan kernel writes the CDF of accumulator k: p[k][s*stride + n]
 struct ScanOut { double* p[4]; long stride; };
 
+// optional in-flight |grad q|^2 integrand for bin_accumulate_impl (adds one
+// accumulator after the explicit integrands); rcos/dphi from row_metrics().
+struct StencilArgs { int ny, nx; const double* rcos; const double* dphi; double dlambda; };
+int row_metrics(const double* lat_rad, int ny, double* rcos, double* dphi, void* stream);
+
 int bin_accumulate_impl(const void* q, int q_dtype, long S, long P,
                         const double* edges, long edges_stride, int N,
                         int closed_right,
@@ -17,6 +22,7 @@ int bin_accumulate_impl(const void* q, int q_dtype, long S, long P,
                         int n_int, const uint8_t* q_mask,
                         int scan_mode, const int32_t* decreasing,
                         double* pdf, const ScanOut& so, int32_t* bin_idx,
-                        void* workspace, size_t ws_bytes, void* stream);
+                        void* workspace, size_t ws_bytes, void* stream,
+                        const StencilArgs* stencil = nullptr);
 
 }  // namespace xc

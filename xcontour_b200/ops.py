@@ -52,6 +52,8 @@ def to_dev(x, dtype=None):
         a = np.ascontiguousarray(x)
         if a.dtype.byteorder == ">":
             a = a.astype(a.dtype.newbyteorder("="))
+        if not a.flags.writeable:
+            a = a.copy()
         t = torch.from_numpy(a)
     elif hasattr(x, "__dlpack__"):
         t = torch.from_dlpack(x)

@@ -42,7 +42,7 @@ class KeffLwaPlan(object):
     table, LWA weights -- built once, reused for every batch."""
 
     def __init__(self, lat_deg, lon_deg, dA, N, increase=True, lt=True,
-                 dtype=np.float32, keff_mask=1e5, part="all", mask=None):
+                 dtype=np.float32, keff_mask=1e5, part="all", mask=None, sub_batch=0):
         ops.require_cuda()
         lat = np.asarray(lat_deg)
         lon = np.asarray(lon_deg)
@@ -50,6 +50,7 @@ class KeffLwaPlan(object):
         self.increase, self.lt = bool(increase), bool(lt)
         self.ctr_dtype = XC_F32 if np.dtype(dtype) == np.float32 else XC_F64
         self.keff_mask, self.part = float(keff_mask), PART[part]
+        self.sub_batch = int(sub_batch)
         dA = np.ascontiguousarray(np.broadcast_to(np.asarray(dA), (self.ny, self.nx)))
         self.dA = ops.to_dev(dA)
         self.ww = ops.lwa_weights(self.dA.reshape(-1))
@@ -83,9 +84,11 @@ class KeffLwaPlan(object):
             out["lwa"] = torch.empty((S, self.ny, self.nx), dtype=torch.float64, device=dev)
         return out
 
-    def run(self, q, grdS=None, out=None, ws=None):
+    def run(self, q, grdS=None, out=None, ws=None, stage_ms=None):
         """q[S, ny, nx] (fp32/fp64, on the GPU) -> dict of device tensors.
-        grdS=None computes |grad q|^2 on the fly with the lat-lon stencil."""
+        grdS=None computes |grad q|^2 on the fly with the lat-lon stencil.
+        stage_ms: optional ctypes float array of N_STAGES entries that receives the
+        per-stage device time (makes the call synchronous)."""
         lib = ops.require_cuda()
         S = q.shape[0]
         assert q.is_cuda and q.is_contiguous() and tuple(q.shape[1:]) == (self.ny, self.nx)
@@ -106,11 +109,12 @@ class KeffLwaPlan(object):
         a.lat_rad, a.dlambda = self.lat_rad.data_ptr(), self.dlambda
         a.table, a.table_coord, a.n_table = self.table.data_ptr(), self.table_coord.data_ptr(), self.ny
         a.eq_coord, a.ww = self.eq_coord.data_ptr(), self.ww.data_ptr()
-        a.keff_mask, a.part = self.keff_mask, self.part
+        a.keff_mask, a.part, a.sub_batch = self.keff_mask, self.part, self.sub_batch
         for k in CONTOUR_VARS:
             setattr(a, k, out[k].data_ptr() if k in out else None)
         a.Qref = out["Qref"].data_ptr() if "Qref" in out else None
         a.lwa = out["lwa"].data_ptr() if "lwa" in out else None
+        a.stage_ms = ctypes.cast(stage_ms, ctypes.c_void_p) if stage_ms is not None else None
         check(lib.xc_keff_lwa_batch(ctypes.byref(a), ctypes.c_void_p(ws.data_ptr()), nb, ops.stream_ptr()))
         return out
 
