@@ -449,26 +449,25 @@ def cal_local_wave_activity_fast(q, Q, dA, coord, increase, part="all"):
 def squared_gradient_latlon(q, lat_deg, lon_deg):
     """Centred finite differences on a regular lat-lon grid, periodic in
     longitude, one-sided at the first/last latitude:
-        |grad q|^2 = (dq/dx)^2 + (dq/dy)^2,  dx = R cos(phi) dlambda, dy = R dphi.
+        dq/dx = (q[j,i+1] - q[j,i-1]) * cx[j],  cx = 1 / ((2 dlambda) * (R cos phi_j))
+        dq/dy = (q[j+1,i] - q[j-1,i]) * cy[j],  cy = 1 / ((phi_{j+1} - phi_{j-1}) * R)
+        |grad q|^2 = (dq/dx)^2 + (dq/dy)^2
     The reference obtains this field from external packages whose source is not
     under /root/reference (xinvert / GeoApps, tests/test_Keff_ocean.py:31-32),
-    so its parity is UNPINNED; this is the definition the CUDA stencil follows.
-    Computation in fp64, result fp64."""
+    so its parity is UNPINNED; this is the definition the CUDA stencil follows
+    (same operation order, fp64 throughout)."""
     q = np.asarray(q, dtype=np.float64)
     phi = np.deg2rad(np.asarray(lat_deg, dtype=np.float64))
     lam = np.deg2rad(np.asarray(lon_deg, dtype=np.float64))
     dlam = lam[1] - lam[0]
     ny = q.shape[-2]
-    dqdx = (np.roll(q, -1, axis=-1) - np.roll(q, 1, axis=-1)) / (2.0 * dlam)
-    cosphi = np.cos(phi)
-    dqdx = dqdx / (Rearth * cosphi)[:, None]
-    dqdy = np.empty_like(q)
-    dqdy[..., 1:-1, :] = (q[..., 2:, :] - q[..., :-2, :]) / \
-        (phi[2:] - phi[:-2])[:, None]
-    dqdy[..., 0, :] = (q[..., 1, :] - q[..., 0, :]) / (phi[1] - phi[0])
-    dqdy[..., ny - 1, :] = (q[..., ny - 1, :] - q[..., ny - 2, :]) / \
-        (phi[ny - 1] - phi[ny - 2])
-    dqdy = dqdy / Rearth
+    jm = np.maximum(np.arange(ny) - 1, 0)
+    jp = np.minimum(np.arange(ny) + 1, ny - 1)
+    with np.errstate(divide="ignore"):
+        cx = 1.0 / ((2.0 * dlam) * (Rearth * np.cos(phi)))
+        cy = 1.0 / ((phi[jp] - phi[jm]) * Rearth)
+    dqdx = (np.roll(q, -1, axis=-1) - np.roll(q, 1, axis=-1)) * cx[:, None]
+    dqdy = (q[..., jp, :] - q[..., jm, :]) * cy[:, None]
     return dqdx * dqdx + dqdy * dqdy
 
 

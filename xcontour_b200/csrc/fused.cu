@@ -93,8 +93,8 @@ extern "C" int xc_keff_lwa_batch(const xc_keff_lwa_args* a, void* workspace, siz
     double* dphi = ar.take<double>((size_t)ny);
     XC_REQUIRE(ar.ok(), "xc_keff_lwa_batch: workspace accounting error");
 
-    StencilArgs sa; sa.ny = ny; sa.nx = nx; sa.rcos = rcos; sa.dphi = dphi; sa.dlambda = a->dlambda;
-    if (stencil) { if (row_metrics(a->lat_rad, ny, rcos, dphi, stream)) return 1; }
+    StencilArgs sa; sa.ny = ny; sa.nx = nx; sa.cx = rcos; sa.cy = dphi;
+    if (stencil) { if (row_metrics(a->lat_rad, ny, a->dlambda, rcos, dphi, stream)) return 1; }
     // optional per-stage timing
     cudaStream_t st = (cudaStream_t)stream;
     const long npass = (S + pl.sub - 1) / pl.sub;

@@ -11,14 +11,11 @@
 
 namespace xc {
 
-__global__ void k_row_metrics(const double* __restrict__ lat_rad, int ny, double* __restrict__ rcos,
-                              double* __restrict__ dphi)
+__global__ void k_row_metrics(const double* __restrict__ lat_rad, int ny, double two_dlam,
+                              double* __restrict__ cx, double* __restrict__ cy)
 {
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < ny; j += gridDim.x * blockDim.x) {
-        rcos[j] = __dmul_rn(kRearthG, cos(lat_rad[j]));
-        const int jm = j == 0 ? 0 : j - 1, jp = j == ny - 1 ? ny - 1 : j + 1;
-        dphi[j] = __dsub_rn(lat_rad[jp], lat_rad[jm]);
-    }
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < ny; j += gridDim.x * blockDim.x)
+        grad2_row_metrics(lat_rad, j, ny, two_dlam, cx[j], cy[j]);
 }
 
 template <typename QT, typename OT>
@@ -28,16 +25,11 @@ k_grad2(const QT* __restrict__ q, int ny, int nx, const double* __restrict__ lat
 {
     const long s = blockIdx.z; const int j = blockIdx.y;
     __shared__ double m[2];
-    if (threadIdx.x == 0) {
-        m[0] = __dmul_rn(kRearthG, cos(lat_rad[j]));
-        const int jm = j == 0 ? 0 : j - 1, jp = j == ny - 1 ? ny - 1 : j + 1;
-        m[1] = __dsub_rn(lat_rad[jp], lat_rad[jm]);
-    }
+    if (threadIdx.x == 0) grad2_row_metrics(lat_rad, j, ny, __dmul_rn(2.0, dlam), m[0], m[1]);
     __syncthreads();
     const QT* qs = q + s * (long)ny * nx;
-    const double two_dlam = __dmul_rn(2.0, dlam);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += gridDim.x * blockDim.x) {
-        double g = grad2_cell(qs, j, i, ny, nx, m[0], m[1], two_dlam);
+        double g = grad2_cell(qs, j, i, ny, nx, m[0], m[1]);
         out[(s * ny + j) * (long)nx + i] = (OT)g;
     }
 }
@@ -46,9 +38,9 @@ k_grad2(const QT* __restrict__ q, int ny, int nx, const double* __restrict__ lat
 
 using namespace xc;
 
-int xc::row_metrics(const double* lat_rad, int ny, double* rcos, double* dphi, void* stream)
+int xc::row_metrics(const double* lat_rad, int ny, double dlambda, double* cx, double* cy, void* stream)
 {
-    k_row_metrics<<<(ny + 255) / 256, 256, 0, (cudaStream_t)stream>>>(lat_rad, ny, rcos, dphi);
+    k_row_metrics<<<(ny + 255) / 256, 256, 0, (cudaStream_t)stream>>>(lat_rad, ny, 2.0 * dlambda, cx, cy);
     XC_LAUNCH_OK();
     return 0;
 }

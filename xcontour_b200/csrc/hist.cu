@@ -17,6 +17,7 @@
 #include "internal.h"
 #include "grad2.cuh"
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace xc {
 
@@ -29,37 +30,44 @@ struct HistParams {
     const void* integ[XC_MAX_INTEGRANDS]; int integ_f32[XC_MAX_INTEGRANDS]; int n_int;
     const uint8_t* q_mask;
     // in-flight |grad q|^2 integrand (last accumulator slot) -- see grad2.cuh
-    int stencil; int ny, nx; const double* rcos; const double* dphi; double two_dlam;
+    int stencil; int ny, nx; const double* cx; const double* cy;
     double* part;            // [S][C][K][N]
     int32_t* bin_idx;        // [S][P] or null
     int ncopy;
 };
 
-struct EdgeGuess { double base, inv; int off; int uniform; };
+struct EdgeGuess { double base, inv; float basef, invf; int off; int uniform; };
 
 // Exact digitize against ascending e[0..N]; -1 when the cell is discarded.
-__device__ __forceinline__ int find_bin(double v, const double* e, int N,
+// Uniform edges: an fp32 guess of the bin, then the guess is walked to the bin
+// whose true fp64 edges bracket v (usually zero or one step) -- the comparisons
+// against e[] decide, the arithmetic never does.
+__device__ __forceinline__ int find_bin(double v, float vf, const double* e, int N,
                                         const EdgeGuess& g, int closed_right)
 {
-    if (closed_right) { if (!(v > e[0]) || !(v <= e[N])) return -1; }
-    else              { if (!(v >= e[0]) || !(v < e[N])) return -1; }
+    if (vf != vf) return -1;
     int p;
     if (g.uniform) {
-        double t = (v - g.base) * g.inv;
-        p = g.off + (int)fmin(fmax(t, -1.0), (double)N);
+        const float t = (vf - g.basef) * g.invf;
+        p = g.off + __float2int_rd(fminf(fmaxf(t, -1.0f), (float)N));
         p = min(max(p, 0), N - 1);
-        if (closed_right) { while (v <= e[p]) --p; while (v > e[p + 1]) ++p; }
-        else              { while (v <  e[p]) --p; while (v >= e[p + 1]) ++p; }
-    } else {
-        int lo = 0, hi = N;            // first index with e[idx] > v  (or >= v)
-        while (lo < hi) {
-            int mid = (lo + hi) >> 1;
-            bool right = closed_right ? (e[mid] < v) : (e[mid] <= v);
-            if (right) lo = mid + 1; else hi = mid;
+        for (;;) {
+            const double lo = e[p], hi = e[p + 1];
+            const int d = closed_right ? ((v > hi) - (v <= lo)) : ((v >= hi) - (v < lo));
+            if (d == 0) return p;
+            p += d;
+            if (p < 0 || p >= N) return -1;
         }
-        p = lo - 1;
     }
-    return p;
+    if (closed_right) { if (!(v > e[0]) || !(v <= e[N])) return -1; }
+    else              { if (!(v >= e[0]) || !(v < e[N])) return -1; }
+    int lo = 0, hi = N;                // first index with e[idx] > v  (or >= v)
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        bool right = closed_right ? (e[mid] < v) : (e[mid] <= v);
+        if (right) lo = mid + 1; else hi = mid;
+    }
+    return lo - 1;
 }
 
 template <int K>
@@ -79,36 +87,73 @@ __device__ __forceinline__ void rmw_add(double* h, const double (&w)[K])
     }
 }
 
-// Warp-collective scatter-add into a warp-private histogram (all 32 lanes must
-// call).  Lanes with the same bin are serialised by the tag protocol.
-template <int K>
-__device__ __forceinline__ void scatter_private(double* H, uint8_t* tag, int bin,
-                                                const double (&w)[K], bool active, int lane)
-{
-    unsigned pending = __ballot_sync(XC_FULL, active);
-    while (pending) {
-        if (active) tag[bin] = (uint8_t)lane;
-        __syncwarp();
-        if (active && tag[bin] == (uint8_t)lane) {
-            rmw_add<K>(H + (size_t)bin * K, w);
-            active = false;
-        }
-        __syncwarp();
-        pending = __ballot_sync(XC_FULL, active);
-    }
-}
+enum { HIST_TAG = 0, HIST_MATCH = 1, HIST_ATOMIC = 2 };
 
-template <int K>
-__device__ __forceinline__ void scatter_atomic(double* H, int bin, const double (&w)[K], bool active)
+// Warp-collective scatter-add of 4 items per lane into a warp-private histogram
+// (all 32 lanes must call).  Lanes that hit the same bin are serialised:
+//   HIST_MATCH: four independent MATCH.ANY give each item the mask of its peers;
+//               per round the lowest remaining peer of every group does a plain
+//               128-bit read-modify-write, all members then clear that bit.
+//   HIST_TAG  : byte-tag protocol (write lane id, winner reads its own id back).
+template <int K, int MODE>
+__device__ __forceinline__ void scatter_add4(double* H, uint8_t* tag, const int (&bin)[4],
+                                             const double (&w)[4][K], int lane)
 {
-    if (active) {
+    if (MODE == HIST_MATCH) {
+        unsigned peers[4];
 #pragma unroll
-        for (int k = 0; k < K; ++k) atomicAdd(H + (size_t)bin * K + k, w[k]);
+        for (int u = 0; u < 4; ++u) {
+            const bool a = bin[u] >= 0;
+            peers[u] = __match_any_sync(XC_FULL, a ? (unsigned)bin[u] : (0x80000000u | (unsigned)lane));
+            if (!a) peers[u] = 0u;
+        }
+        unsigned more;
+        do {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (peers[u] && (__ffs(peers[u]) - 1) == lane) rmw_add<K>(H + (size_t)bin[u] * K, w[u]);
+                peers[u] &= peers[u] - 1u;
+                __syncwarp();
+            }
+            more = peers[0] | peers[1] | peers[2] | peers[3];
+        } while (__any_sync(XC_FULL, more != 0u));
+    } else if (MODE == HIST_TAG) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            bool active = bin[u] >= 0;
+            unsigned pending = __ballot_sync(XC_FULL, active);
+            while (pending) {
+                if (active) tag[bin[u]] = (uint8_t)lane;
+                __syncwarp();
+                if (active && tag[bin[u]] == (uint8_t)lane) {
+                    rmw_add<K>(H + (size_t)bin[u] * K, w[u]);
+                    active = false;
+                }
+                __syncwarp();
+                pending = __ballot_sync(XC_FULL, active);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (bin[u] >= 0) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) atomicAdd(H + (size_t)bin[u] * K + k, w[u][k]);
+            }
     }
 }
 
-// grid = (C, nslices).  PRIVATE: one histogram copy per warp, no atomics.
-template <typename QT, int K, bool PRIVATE>
+// w[k] = x with k only known at run time, without spilling w to local memory
+template <int K>
+__device__ __forceinline__ void put(double (&w)[K], int& k, double x)
+{
+#pragma unroll
+    for (int kk = 0; kk < K; ++kk) if (kk == k) w[kk] = x;
+    ++k;
+}
+
+// grid = (C, nslices).  MODE != HIST_ATOMIC: one histogram copy per warp, no atomics.
+template <typename QT, int K, int MODE>
 __global__ void __launch_bounds__(HIST_MAX_WARPS * 32)
 k_hist(const HistParams p)
 {
@@ -140,6 +185,8 @@ k_hist(const HistParams p)
         for (int k = a + tid; k <= b; k += blockDim.x)
             if (fabs(e[k] - (g.base + (double)(k - a) * h)) > h) bad = 1;
         g.uniform = !__syncthreads_or(bad);
+        g.basef = (float)g.base; g.invf = (float)g.inv;
+        if (!isfinite(g.invf) || !isfinite(g.basef)) g.uniform = 0;
     }
 
     const QT* qs = reinterpret_cast<const QT*>(p.q) + s * p.P;
@@ -148,11 +195,15 @@ k_hist(const HistParams p)
     double*  Hw   = H + (size_t)(warp % p.ncopy) * N * K;
     uint8_t* tagw = tags + (size_t)warp * tagN;
     const bool vec_ok = ((p.P & 3) == 0) && ((((uintptr_t)p.q) & 15) == 0);
+    // 4 consecutive cells share a row when nx % 4 == 0: the stencil then needs one
+    // 128-bit load from the row above, one from the row below and two scalars
+    const bool st_vec = p.stencil && vec_ok && ((p.nx & 3) == 0) && sizeof(QT) == 4;
 
     for (long base = beg + (long)warp * 128; base < end; base += (long)nwarps * 128) {
         const long i0 = base + lane * 4;
+        const bool full = vec_ok && i0 + 3 < end;
         QT qv[4];
-        if (vec_ok && i0 + 3 < end) {
+        if (full) {
             if (sizeof(QT) == 4) {
                 float4 t = __ldg(reinterpret_cast<const float4*>(qs + i0));
                 qv[0] = t.x; qv[1] = t.y; qv[2] = t.z; qv[3] = t.w;
@@ -165,58 +216,100 @@ k_hist(const HistParams p)
 #pragma unroll
             for (int u = 0; u < 4; ++u) qv[u] = (i0 + u < end) ? __ldg(qs + i0 + u) : (QT)CUDART_NAN;
         }
+        // weights of the 4 cells
+        double ad[4]; float af[4];
+        if (full && p.dA_f32) {
+            float4 t = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.dA) + i0));
+            af[0] = t.x; af[1] = t.y; af[2] = t.z; af[3] = t.w;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ad[u] = (double)af[u];
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                af[u] = 0.f; ad[u] = 0.0;
+                if (i0 + u < end) {
+                    if (p.dA_f32) { af[u] = __ldg(reinterpret_cast<const float*>(p.dA) + i0 + u); ad[u] = (double)af[u]; }
+                    else          { ad[u] = __ldg(reinterpret_cast<const double*>(p.dA) + i0 + u); }
+                }
+            }
+        }
+        double gq[4] = {0.0, 0.0, 0.0, 0.0};
+        if (p.stencil && i0 < end) {
+            const int j = (int)((unsigned long long)i0 / (unsigned)p.nx);
+            const int col = (int)(i0 - (long)j * p.nx);
+            if (st_vec && full) {
+                const int jm = j == 0 ? 0 : j - 1, jp = j == p.ny - 1 ? p.ny - 1 : j + 1;
+                const float4 nn = __ldg(reinterpret_cast<const float4*>(qs + (long)jp * p.nx + col));
+                const float4 ss = __ldg(reinterpret_cast<const float4*>(qs + (long)jm * p.nx + col));
+                const float wv = __ldg(reinterpret_cast<const float*>(qs) + (long)j * p.nx + (col == 0 ? p.nx - 1 : col - 1));
+                const float ev = __ldg(reinterpret_cast<const float*>(qs) + (long)j * p.nx + (col + 4 == p.nx ? 0 : col + 4));
+                const double cx = __ldg(p.cx + j), cy = __ldg(p.cy + j);
+                const double c0 = (double)qv[0], c1 = (double)qv[1], c2 = (double)qv[2], c3 = (double)qv[3];
+                gq[0] = grad2_from(c1, (double)wv, (double)nn.x, (double)ss.x, cx, cy);
+                gq[1] = grad2_from(c2, c0, (double)nn.y, (double)ss.y, cx, cy);
+                gq[2] = grad2_from(c3, c1, (double)nn.z, (double)ss.z, cx, cy);
+                gq[3] = grad2_from((double)ev, c2, (double)nn.w, (double)ss.w, cx, cy);
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (i0 + u < end) {
+                        int jj = j, cu = col + u;
+                        while (cu >= p.nx) { cu -= p.nx; ++jj; }
+                        gq[u] = grad2_cell(qs, jj, cu, p.ny, p.nx, __ldg(p.cx + jj), __ldg(p.cy + jj));
+                    }
+                }
+            }
+        }
         int bins[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const long i = i0 + u;
             bool ok = i < end;
             if (ok && p.q_mask) ok = p.q_mask[i] != 0;
-            bins[u] = ok ? find_bin((double)qv[u], e, N, g, p.closed_right) : -1;
+            bins[u] = ok ? find_bin((double)qv[u], (float)qv[u], e, N, g, p.closed_right) : -1;
         }
         if (p.bin_idx) {
             int32_t* bo = p.bin_idx + s * p.P;
 #pragma unroll
             for (int u = 0; u < 4; ++u) if (i0 + u < end) bo[i0 + u] = bins[u];
         }
+        double w[4][K];
+        const bool fast_layout = (K == 2) && p.acc_area && p.n_int == 0 && p.stencil;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const long i = i0 + u;
             const bool act = bins[u] >= 0;
-            double w[K];
 #pragma unroll
-            for (int k = 0; k < K; ++k) w[k] = 0.0;
-            if (act) {
+            for (int k = 0; k < K; ++k) w[u][k] = 0.0;
+            if (fast_layout) {                       // {dA, |grad q|^2 dA}: the fused Keff pass
+                const double pr = __dmul_rn(gq[u], ad[u]);
+                w[u][0] = isnan(ad[u]) ? 0.0 : ad[u];
+                w[u][K - 1] = isnan(pr) ? 0.0 : pr;
+            } else if (act) {
                 int k = 0;
-                float  af = 0.f; double ad = 0.0;
-                if (p.dA_f32) { af = __ldg(reinterpret_cast<const float*>(p.dA) + i); ad = (double)af; }
-                else          { ad = __ldg(reinterpret_cast<const double*>(p.dA) + i); }
-                if (p.acc_area) { w[k++] = isnan(ad) ? 0.0 : ad; }
+                if (p.acc_area) put<K>(w[u], k, isnan(ad[u]) ? 0.0 : ad[u]);
 #pragma unroll
                 for (int n = 0; n < XC_MAX_INTEGRANDS; ++n) {
-                    if (n < p.n_int && k < K) {
+                    if (n < p.n_int) {
                         double pr;
                         if (p.integ_f32[n]) {
                             float gf = __ldg(reinterpret_cast<const float*>(p.integ[n]) + s * p.P + i);
                             // product rounded in the common dtype (core.py:444)
-                            pr = p.dA_f32 ? (double)__fmul_rn(gf, af) : __dmul_rn((double)gf, ad);
+                            pr = p.dA_f32 ? (double)__fmul_rn(gf, af[u]) : __dmul_rn((double)gf, ad[u]);
                         } else {
                             double gd = __ldg(reinterpret_cast<const double*>(p.integ[n]) + s * p.P + i);
-                            pr = __dmul_rn(gd, ad);
+                            pr = __dmul_rn(gd, ad[u]);
                         }
-                        w[k++] = isnan(pr) ? 0.0 : pr;             // fillna(0), core.py:449
+                        put<K>(w[u], k, isnan(pr) ? 0.0 : pr);     // fillna(0), core.py:449
                     }
                 }
-                if (p.stencil && k < K) {
-                    const int j = (int)(i / p.nx), col = (int)(i - (long)j * p.nx);
-                    const double gq = grad2_cell(qs, j, col, p.ny, p.nx, __ldg(p.rcos + j),
-                                                 __ldg(p.dphi + j), p.two_dlam);
-                    const double pr = __dmul_rn(gq, ad);
-                    w[k++] = isnan(pr) ? 0.0 : pr;
+                if (p.stencil) {
+                    const double pr = __dmul_rn(gq[u], ad[u]);
+                    put<K>(w[u], k, isnan(pr) ? 0.0 : pr);
                 }
             }
-            if (PRIVATE) scatter_private<K>(Hw, tagw, bins[u], w, act, lane);
-            else         scatter_atomic<K>(Hw, bins[u], w, act);
         }
+        scatter_add4<K, MODE>(Hw, tagw, bins, w, lane);
     }
     __syncthreads();
     double* out = p.part + ((size_t)(blockIdx.y + p.s0) * C + c) * K * N;
@@ -245,7 +338,17 @@ k_reduce_scan(const double* __restrict__ part, int C, int K, int N, int scan_mod
 
     for (int n = tid; n < N; n += blockDim.x) {
         double acc = 0.0;
-        for (int c = 0; c < C; ++c) acc += part[(((size_t)s * C + c) * K + k) * N + n];
+        const double* pp = part + ((size_t)s * C * K + k) * N + n;
+        const size_t cs = (size_t)K * N;
+        int c = 0;
+        for (; c + 8 <= C; c += 8) {                 // 8 loads in flight, summed in order
+            double t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = pp[(size_t)(c + u) * cs];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc += t[u];
+        }
+        for (; c < C; ++c) acc += pp[(size_t)c * cs];
         pd[suffix ? N - 1 - n : n] = acc;
         if (pdf) pdf[((size_t)s * K + k) * N + (rev ? N - 1 - n : n)] = acc;
     }
@@ -308,21 +411,30 @@ static HistPlan plan_hist(long S, long P, int N, int K)
     return pl;
 }
 
+static bool hist_use_match()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("XCB200_HIST_DEDUP"); v = (e && e[0] == 't') ? 0 : 1; }
+    return v == 1;
+}
+
+template <typename QT, int K, int MODE>
+static int launch_hist_mode(const HistParams& hp, const HistPlan& pl, long ns, cudaStream_t st)
+{
+    dim3 grid((unsigned)pl.C, (unsigned)ns);
+    XC_CUDA_OK(cudaFuncSetAttribute(k_hist<QT, K, MODE>,
+               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    k_hist<QT, K, MODE><<<grid, pl.warps * 32, pl.smem, st>>>(hp);
+    XC_LAUNCH_OK();
+    return 0;
+}
+
 template <typename QT, int K>
 static int launch_hist(const HistParams& hp, const HistPlan& pl, long ns, cudaStream_t st)
 {
-    dim3 grid((unsigned)pl.C, (unsigned)ns);
-    if (pl.priv) {
-        XC_CUDA_OK(cudaFuncSetAttribute(k_hist<QT, K, true>,
-                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-        k_hist<QT, K, true><<<grid, pl.warps * 32, pl.smem, st>>>(hp);
-    } else {
-        XC_CUDA_OK(cudaFuncSetAttribute(k_hist<QT, K, false>,
-                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-        k_hist<QT, K, false><<<grid, pl.warps * 32, pl.smem, st>>>(hp);
-    }
-    XC_LAUNCH_OK();
-    return 0;
+    if (!pl.priv) return launch_hist_mode<QT, K, HIST_ATOMIC>(hp, pl, ns, st);
+    return hist_use_match() ? launch_hist_mode<QT, K, HIST_MATCH>(hp, pl, ns, st)
+                            : launch_hist_mode<QT, K, HIST_TAG>(hp, pl, ns, st);
 }
 
 }  // namespace xc
@@ -394,9 +506,8 @@ int xc::bin_accumulate_impl(const void* q, int q_dtype, long S, long P,
     hp.q_mask = q_mask;
     hp.stencil = stencil ? 1 : 0;
     if (stencil) {
-        hp.ny = stencil->ny; hp.nx = stencil->nx; hp.rcos = stencil->rcos; hp.dphi = stencil->dphi;
-        hp.two_dlam = 2.0 * stencil->dlambda;
-    } else { hp.ny = hp.nx = 0; hp.rcos = hp.dphi = nullptr; hp.two_dlam = 0.0; }
+        hp.ny = stencil->ny; hp.nx = stencil->nx; hp.cx = stencil->cx; hp.cy = stencil->cy;
+    } else { hp.ny = hp.nx = 0; hp.cx = hp.cy = nullptr; }
     hp.part = ar.take<double>((size_t)S * pl.C * K * N);
     hp.bin_idx = bin_idx;
     hp.ncopy = pl.ncopy;

@@ -11,8 +11,8 @@ struct ScanOut { double* p[4]; long stride; };
 
 // optional in-flight |grad q|^2 integrand for bin_accumulate_impl (adds one
 // accumulator after the explicit integrands); rcos/dphi from row_metrics().
-struct StencilArgs { int ny, nx; const double* rcos; const double* dphi; double dlambda; };
-int row_metrics(const double* lat_rad, int ny, double* rcos, double* dphi, void* stream);
+struct StencilArgs { int ny, nx; const double* cx; const double* cy; };
+int row_metrics(const double* lat_rad, int ny, double dlambda, double* cx, double* cy, void* stream);
 
 int bin_accumulate_impl(const void* q, int q_dtype, long S, long P,
                         const double* edges, long edges_stride, int N,

@@ -17,6 +17,7 @@
 // Profiles that are not sorted (or contain NaN) take the exact O(n_eq^2) kernel.
 #include "common.cuh"
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace xc {
 
@@ -39,11 +40,14 @@ __global__ void k_check_sorted(const double* __restrict__ Q, int ny, int increas
     if (threadIdx.x == 0) flag[s] = bad ? 0 : 1;
 }
 
+constexpr int LWA_BIG = 128;      // rows staged per block (4 warp-steps of 32 rows)
+constexpr int LWA_RS  = 130;      // staging row stride; == 2 (mod 32) keeps the transposed store conflict-free
+
 struct LwaSmem {
     size_t off_Q, off_D, off_lut, off_tag, off_sq, off_sw, total;
     int nyp, tagp;
 };
-static __host__ __device__ inline LwaSmem lwa_layout(int ny, int TC)
+static __host__ __device__ inline LwaSmem lwa_layout(int ny, int TC, int qbytes, bool tags)
 {
     LwaSmem L;
     L.nyp = ny + 2;
@@ -51,11 +55,12 @@ static __host__ __device__ inline LwaSmem lwa_layout(int ny, int TC)
     size_t o = 0;
     L.off_Q = o;   o += (size_t)((ny + 1) & ~1) * 8;
     L.off_D = o;   o += (size_t)TC * L.nyp * 16;
-    L.off_sq = o;  o += (size_t)32 * (TC + 1) * 8;
-    L.off_sw = o;  o += (size_t)32 * (TC + 1) * 8;
+    L.off_sw = o;  o += (size_t)TC * LWA_RS * 8;
+    L.off_sq = o;  o += (size_t)TC * LWA_RS * qbytes;
+    o = (o + 15) & ~(size_t)15;
     L.off_lut = o; o += (size_t)(LWA_LUT + 2) * 2;
     o = (o + 15) & ~(size_t)15;
-    L.off_tag = o; o += (size_t)TC * L.tagp;
+    L.off_tag = o; if (tags) o += (size_t)TC * L.tagp;
     L.total = o;
     return L;
 }
@@ -67,8 +72,58 @@ __device__ __forceinline__ int lwa_bucket(double v, double qmin, double scale)
     return b < 0 ? 0 : b;
 }
 
-// grid = (ceil(nx/TC), nslices), block = TC warps.
-template <typename QT>
+// Warp-private scatter-add of -(w, wv) into Dw[target] for the lanes with
+// act == true; lanes that share a target are serialised.
+//   MATCH: one MATCH.ANY gives every lane the mask of its peers; the lowest
+//          remaining peer of each group does a plain read-modify-write per
+//          round, every member then clears that bit.
+//   tags : every pending lane writes its id into a byte tag of the target, the
+//          lane that reads its own id back owns the slot for this round.
+template <bool MATCH>
+__device__ __forceinline__ void lwa_scatter_sub4(double2* Dw, uint8_t* tagw, const int (&target)[4],
+                                                 const double (&w)[4], const double (&wv)[4],
+                                                 const bool (&act)[4], int lane)
+{
+    if (MATCH) {
+        unsigned peers[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            peers[u] = __match_any_sync(XC_FULL, act[u] ? (unsigned)target[u] : (0x80000000u | (unsigned)lane));
+            if (!act[u]) peers[u] = 0u;
+        }
+        unsigned more;
+        do {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (peers[u] && (__ffs(peers[u]) - 1) == lane) {
+                    double2 t = Dw[target[u]]; t.x -= w[u]; t.y -= wv[u]; Dw[target[u]] = t;
+                }
+                peers[u] &= peers[u] - 1u;
+                __syncwarp();
+            }
+            more = peers[0] | peers[1] | peers[2] | peers[3];
+        } while (__any_sync(XC_FULL, more != 0u));
+    } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            bool a = act[u];
+            unsigned pending = __ballot_sync(XC_FULL, a);
+            while (pending) {
+                if (a) tagw[target[u]] = (uint8_t)lane;
+                __syncwarp();
+                if (a && tagw[target[u]] == (uint8_t)lane) {
+                    double2 t = Dw[target[u]]; t.x -= w[u]; t.y -= wv[u]; Dw[target[u]] = t;
+                    a = false;
+                }
+                __syncwarp();
+                pending = __ballot_sync(XC_FULL, a);
+            }
+        }
+    }
+}
+
+// grid = (ceil(nx/TC), nslices), block = TC warps; warp w owns column i0 + w.
+template <typename QT, bool MATCH>
 __global__ void __launch_bounds__(LWA_MAX_TC * 32)
 k_lwa_fast(const QT* __restrict__ q, long s0, int ny, int nx,
            const double* __restrict__ Qref, const double* __restrict__ ww,
@@ -78,11 +133,11 @@ k_lwa_fast(const QT* __restrict__ q, long s0, int ny, int nx,
     const long s = s0 + blockIdx.y;
     if (!sorted[s]) return;
     extern __shared__ __align__(16) unsigned char smem[];
-    const LwaSmem L = lwa_layout(ny, TC);
+    const LwaSmem L = lwa_layout(ny, TC, (int)sizeof(QT), !MATCH);
     double*   Qs  = reinterpret_cast<double*>(smem + L.off_Q);
     double2*  D   = reinterpret_cast<double2*>(smem + L.off_D);
-    double*   sq  = reinterpret_cast<double*>(smem + L.off_sq);    // [32][TC+1]
-    double*   sw  = reinterpret_cast<double*>(smem + L.off_sw);
+    double*   sw  = reinterpret_cast<double*>(smem + L.off_sw);    // [TC][LWA_RS]
+    QT*       sq  = reinterpret_cast<QT*>(smem + L.off_sq);        // [TC][LWA_RS]
     uint16_t* lut = reinterpret_cast<uint16_t*>(smem + L.off_lut);
     uint8_t*  tag = smem + L.off_tag;
 
@@ -91,6 +146,23 @@ k_lwa_fast(const QT* __restrict__ q, long s0, int ny, int nx,
     const int i0 = blockIdx.x * TC;
     const QT* qs = q + s * (long)ny * nx;
     const double* Qg = Qref + s * (long)ny;
+
+    // staging map: element e = k*nthr + tid of a 128 x TC block -> (row, col);
+    // nthr = 32*TC, so row = 32*k + tid/TC and col = tid%TC for every k
+    const int rr = tid / TC, cc = tid - rr * TC;
+    const bool col_ok = (i0 + cc) < nx;
+    QT pq[4]; double pw[4];
+    auto fetch = [&](int b) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int j = b * LWA_BIG + 32 * k + rr;
+            if (j < ny && col_ok) {
+                pq[k] = __ldg(qs + (long)j * nx + i0 + cc);
+                pw[k] = __ldg(ww + (long)j * nx + i0 + cc);
+            } else { pq[k] = (QT)CUDART_NAN; pw[k] = 0.0; }
+        }
+    };
+    fetch(0);
 
     for (int j = tid; j < ny; j += nthr) Qs[j] = sg * Qg[j];
     for (int k = tid; k < TC * L.nyp; k += nthr) D[k] = make_double2(0.0, 0.0);
@@ -110,91 +182,96 @@ k_lwa_fast(const QT* __restrict__ q, long s0, int ny, int nx,
     const bool use_t1 = (part == XC_PART_ALL) || !keep_pos;   // mask -1 region
     const bool use_t2 = (part == XC_PART_ALL) || keep_pos;    // mask +1 region
 
-    // staging map: thread -> (row rr, column cc) of a 32 x TC chunk
-    const int rr = tid / TC, cc = tid - rr * TC;
-    const bool col_ok = (i0 + cc) < nx;
-    auto fetch = [&](int r0, double& vq, double& vw) {
-        const int j = r0 + rr;
-        if (rr < 32 && j < ny && col_ok) {
-            vq = sg * (double)__ldg(qs + (long)j * nx + i0 + cc);
-            vw = __ldg(ww + (long)j * nx + i0 + cc);
-        } else { vq = CUDART_NAN; vw = 0.0; }
-    };
-    double nq, nw;
-    fetch(0, nq, nw);
     double2* Dw = D + (size_t)warp * L.nyp;
     uint8_t* tagw = tag + (size_t)warp * L.tagp;
+    const QT*     sqw = sq + (size_t)warp * LWA_RS;
+    const double* sww = sw + (size_t)warp * LWA_RS;
+    const int nblk = (ny + LWA_BIG - 1) / LWA_BIG;
 
-    for (int r0 = 0; r0 < ny; r0 += 32) {
-        if (rr < 32) { sq[rr * (TC + 1) + cc] = nq; sw[rr * (TC + 1) + cc] = nw; }
-        __syncthreads();
-        if (r0 + 32 < ny) fetch(r0 + 32, nq, nw);          // prefetch the next chunk
-        const int jp = r0 + lane;
-        const double v = sq[lane * (TC + 1) + warp];
-        const double w = sw[lane * (TC + 1) + warp];
-        bool act = (jp < ny) && !isnan(v) && !isnan(w);
-        int target = 0;
-        if (act) {
-            int lo;
-            if (v < qmin) lo = 0;
-            else if (v > qmax) lo = ny;
-            else {
-                const int b = lwa_bucket(v, qmin, scale);
-                int a = lut[b], e = lut[b + 1];
-                while (a < e) {                              // first idx with Qs >= v
-                    int mid = (a + e) >> 1;
-                    if (Qs[mid] < v) a = mid + 1; else e = mid;
-                }
-                lo = a;
-            }
-            if (lo > jp + 1) { target = lo; act = use_t1; }
-            else {
-                int hi = lo;
-                while (hi < ny && Qs[hi] == v) ++hi;
-                if (hi <= jp) { target = hi; act = use_t2; }
-                else act = false;
-            }
+    for (int b = 0; b < nblk; ++b) {
+        if (b > 0) __syncthreads();                          // everyone is done with the staging buffers
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                        // transposed store: [col][row]
+            sq[cc * LWA_RS + 32 * k + rr] = pq[k];
+            sw[cc * LWA_RS + 32 * k + rr] = pw[k];
         }
-        const double wv = w * v;
-        if (act) {                                           // own slot j'+1: +(w, w v)
-            double2 t = Dw[jp + 1]; t.x += w; t.y += wv; Dw[jp + 1] = t;
+        __syncthreads();
+        if (b + 1 < nblk) fetch(b + 1);                      // next block's loads fly during the work below
+
+        int    tgt[4]; bool act[4]; double wq[4], wvq[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int jp = b * LWA_BIG + 32 * u + lane;
+            const double v = sg * (double)sqw[32 * u + lane];
+            const double w = sww[32 * u + lane];
+            bool a = (jp < ny) && !isnan(v) && !isnan(w);
+            int target = 0;
+            if (a) {
+                int lo;
+                if (v < qmin) lo = 0;
+                else if (v > qmax) lo = ny;
+                else {
+                    const int bk = lwa_bucket(v, qmin, scale);
+                    int x = lut[bk], e = lut[bk + 1];
+#pragma unroll
+                    for (int it = 0; it < 3; ++it) {         // branch-free bisection: covers e - x <= 7
+                        const int mid = (x + e) >> 1;
+                        const bool open = x < e;
+                        const bool below = open && (Qs[open ? mid : 0] < v);
+                        x = below ? mid + 1 : x;
+                        e = (open && !below) ? mid : e;
+                    }
+                    while (x < e) {                          // first idx with Qs >= v
+                        int mid = (x + e) >> 1;
+                        if (Qs[mid] < v) x = mid + 1; else e = mid;
+                    }
+                    lo = x;
+                }
+                if (lo > jp + 1) { target = lo; a = use_t1; }
+                else {
+                    int hi = lo;
+                    while (hi < ny && Qs[hi] == v) ++hi;
+                    if (hi <= jp) { target = hi; a = use_t2; }
+                    else a = false;
+                }
+            }
+            tgt[u] = target; act[u] = a; wq[u] = w; wvq[u] = w * v;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {                        // own slot j'+1: +(w, w v), no conflicts
+            const int jp = b * LWA_BIG + 32 * u + lane;
+            if (act[u]) { double2 t = Dw[jp + 1]; t.x += wq[u]; t.y += wvq[u]; Dw[jp + 1] = t; }
         }
         __syncwarp();
-        {                                                    // far end: -(w, w v)
-            unsigned pending = __ballot_sync(XC_FULL, act);
-            while (pending) {
-                if (act) tagw[target] = (uint8_t)lane;
-                __syncwarp();
-                if (act && tagw[target] == (uint8_t)lane) {
-                    double2 t = Dw[target]; t.x -= w; t.y -= wv; Dw[target] = t;
-                    act = false;
-                }
-                __syncwarp();
-                pending = __ballot_sync(XC_FULL, act);
-            }
-        }
-        __syncthreads();                                     // staging buffers are reused
+        lwa_scatter_sub4<MATCH>(Dw, tagw, tgt, wq, wvq, act, lane);   // far end of the range: -(w, w v)
     }
 
-    // prefix sums down each column, 32 rows per step, then a coalesced store
-    double cS = 0.0, cV = 0.0;
-    double* so = sq;                                         // [32][TC+1] output staging
-    for (int r0 = 0; r0 < ny; r0 += 32) {
-        const int j = r0 + lane;
-        double2 d = (j < ny) ? Dw[j] : make_double2(0.0, 0.0);
-        double xs = d.x, xv = d.y;
+    // prefix sums down the column: each lane owns a contiguous run of rows (odd
+    // length -> conflict-free 128-bit accesses), one warp scan joins the runs;
+    // the result overwrites D in place and is written out with coalesced stores.
+    {
+        const int Lr = ((ny + 31) / 32) | 1;
+        const int j0 = lane * Lr, j1 = min(ny, j0 + Lr);
+        double aS = 0.0, aV = 0.0;
+        for (int j = j0; j < j1; ++j) { double2 d = Dw[j]; aS += d.x; aV += d.y; }
+        double xs = aS, xv = aV;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             double ts = __shfl_up_sync(XC_FULL, xs, o), tv = __shfl_up_sync(XC_FULL, xv, o);
             if (lane >= o) { xs += ts; xv += tv; }
         }
-        xs += cS; xv += cV;
-        cS = __shfl_sync(XC_FULL, xs, 31); cV = __shfl_sync(XC_FULL, xv, 31);
-        if (j < ny) so[lane * (TC + 1) + warp] = sg * (xv - Qs[j] * xs);
-        __syncthreads();
-        if (rr < 32 && r0 + rr < ny && col_ok)
-            out[(s * ny + r0 + rr) * (long)nx + i0 + cc] = so[rr * (TC + 1) + cc];
-        __syncthreads();
+        double rS = xs - aS, rV = xv - aV;                   // exclusive prefix of this lane's run
+        for (int j = j0; j < j1; ++j) {
+            double2 d = Dw[j];
+            rS += d.x; rV += d.y;
+            reinterpret_cast<double*>(Dw + j)[0] = sg * (rV - Qs[j] * rS);
+        }
+    }
+    __syncthreads();
+    if (col_ok) {
+        const double2* Dc = D + (size_t)cc * L.nyp;
+        for (int j = rr; j < ny; j += 32)
+            out[(s * ny + j) * (long)nx + i0 + cc] = Dc[j].x;
     }
 }
 
@@ -301,10 +378,32 @@ __global__ void k_lwa_weights(const void* __restrict__ dA, int is_f32, long P,
 
 using namespace xc;
 
-static int lwa_pick_tc(int ny)
+static bool lwa_use_match()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("XCB200_LWA_DEDUP"); v = (e && e[0] == 't') ? 0 : 1; }
+    return v == 1;
+}
+
+static int lwa_pick_tc(int ny, int qbytes, bool tags)
 {
     for (int tc = LWA_MAX_TC; tc >= 1; --tc)
-        if (lwa_layout(ny, tc).total <= 227 * 1024) return tc;
+        if (lwa_layout(ny, tc, qbytes, tags).total <= 227 * 1024) return tc;
+    return 0;
+}
+
+template <typename QT, bool MATCH>
+static int launch_lwa_fast(const QT* q, long S, int n_eq, int n_x, const double* Qref, const double* ww,
+                           int increase, int part, const int32_t* sorted, double* out, int tc, cudaStream_t st)
+{
+    const LwaSmem L = lwa_layout(n_eq, tc, (int)sizeof(QT), !MATCH);
+    XC_CUDA_OK(cudaFuncSetAttribute(k_lwa_fast<QT, MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    for (long s0 = 0; s0 < S; s0 += 65535) {
+        long ns = S - s0 < 65535 ? S - s0 : 65535;
+        dim3 grid((unsigned)((n_x + tc - 1) / tc), (unsigned)ns);
+        k_lwa_fast<QT, MATCH><<<grid, tc * 32, L.total, st>>>(q, s0, n_eq, n_x, Qref, ww, increase, part, sorted, out, tc);
+        XC_LAUNCH_OK();
+    }
     return 0;
 }
 
@@ -343,27 +442,21 @@ extern "C" int xc_lwa(const void* q, int q_dtype, long S, int n_eq, int n_x,
     cudaStream_t st = (cudaStream_t)stream;
     Arena ar(workspace, ws_bytes);
     int32_t* sorted = ar.take<int32_t>((size_t)S);
-    const int tc = (n_eq < 65535) ? lwa_pick_tc(n_eq) : 0;
+    const bool match = lwa_use_match();
+    const int qbytes = q_dtype == XC_F32 ? 4 : 8;
+    const int tc = (n_eq < 65535) ? lwa_pick_tc(n_eq, qbytes, !match) : 0;
     const bool fast = (variant == 1) && tc >= 1;
     if (fast) {
         k_check_sorted<<<(unsigned)S, 256, 0, st>>>(Qref, n_eq, increase, sorted);
         XC_LAUNCH_OK();
-        const LwaSmem L = lwa_layout(n_eq, tc);
+        int rc;
         if (q_dtype == XC_F32)
-            XC_CUDA_OK(cudaFuncSetAttribute(k_lwa_fast<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+            rc = match ? launch_lwa_fast<float, true>((const float*)q, S, n_eq, n_x, Qref, ww, increase, part, sorted, out, tc, st)
+                       : launch_lwa_fast<float, false>((const float*)q, S, n_eq, n_x, Qref, ww, increase, part, sorted, out, tc, st);
         else
-            XC_CUDA_OK(cudaFuncSetAttribute(k_lwa_fast<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-        for (long s0 = 0; s0 < S; s0 += 65535) {
-            long ns = S - s0 < 65535 ? S - s0 : 65535;
-            dim3 grid((unsigned)((n_x + tc - 1) / tc), (unsigned)ns);
-            if (q_dtype == XC_F32)
-                k_lwa_fast<float><<<grid, tc * 32, L.total, st>>>((const float*)q, s0, n_eq, n_x, Qref, ww,
-                                                                  increase, part, sorted, out, tc);
-            else
-                k_lwa_fast<double><<<grid, tc * 32, L.total, st>>>((const double*)q, s0, n_eq, n_x, Qref, ww,
-                                                                   increase, part, sorted, out, tc);
-            XC_LAUNCH_OK();
-        }
+            rc = match ? launch_lwa_fast<double, true>((const double*)q, S, n_eq, n_x, Qref, ww, increase, part, sorted, out, tc, st)
+                       : launch_lwa_fast<double, false>((const double*)q, S, n_eq, n_x, Qref, ww, increase, part, sorted, out, tc, st);
+        if (rc) return rc;
     }
     // exact loop for whatever the fast path did not take
     dim3 blk(32, 8);
