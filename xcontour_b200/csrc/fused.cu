@@ -40,7 +40,7 @@ FusedPlan fused_plan(long S, int ny, int nx, int N, long sub_req)
     p.sub = sub_req > 0 ? (sub_req < S ? sub_req : S) : auto_sub_batch(S, P);
     p.ws_minmax = xc_minmax_levels_workspace_bytes(p.sub, P);
     p.ws_hist = xc_bin_accumulate_workspace_bytes(p.sub, P, N, 2);
-    p.ws_lwa = xc_lwa_workspace_bytes(p.sub);
+    p.ws_lwa = xc_lwa_workspace_bytes(p.sub) + 512;
     size_t t = 0;
     t += align_up(p.ws_minmax, 256) + align_up(p.ws_hist, 256) + align_up(p.ws_lwa, 256);
     t += align_up((size_t)p.sub * (N + 1) * 8, 256);        // edges
@@ -80,7 +80,8 @@ extern "C" int xc_keff_lwa_batch(const xc_keff_lwa_args* a, void* workspace, siz
     Arena ar(workspace, ws_bytes);
     char* w_minmax = ar.take<char>(pl.ws_minmax);
     char* w_hist = ar.take<char>(pl.ws_hist);
-    char* w_lwa = ar.take<char>(pl.ws_lwa);
+    int32_t* sorted = ar.take<int32_t>((size_t)pl.sub);
+    int32_t* any_unsorted = ar.take<int32_t>(1);
     double* edges = ar.take<double>((size_t)pl.sub * (N + 1));
     int32_t* decr = ar.take<int32_t>((size_t)pl.sub);
     double* t_ctr = ar.take<double>((size_t)pl.sub * N);     double* t_area = ar.take<double>((size_t)pl.sub * N);
@@ -120,38 +121,31 @@ extern "C" int xc_keff_lwa_batch(const xc_keff_lwa_args* a, void* workspace, siz
         double* Qref = a->Qref ? a->Qref + s0 * (long)ny : t_Q;
 
         mark(0);
-        // (1) levels, (1b) edges -- per-slice contours take the per-'time' branch
-        if (xc_minmax_levels(q, a->q_dtype, ns, P, N, a->increase, a->ctr_dtype, ctr, nullptr,
-                             w_minmax, pl.ws_minmax, stream)) return 1;
+        // (1)+(1b) min/max, levels and per-'time'-branch edges in two launches
+        if (minmax_levels_impl(q, a->q_dtype, ns, P, N, a->increase, a->ctr_dtype, ctr, nullptr,
+                               edges, decr, any_unsorted, w_minmax, pl.ws_minmax, stream)) return 1;
         mark(1);
-        if (xc_hist_edges(ctr, ns, N, a->ctr_dtype, 1, edges, decr, stream)) return 1;
         mark(2);
-        // (2) area and int |grad q|^2 dA in one pass over q
-        ScanOut so; so.p[0] = area; so.p[1] = intg; so.p[2] = so.p[3] = nullptr; so.stride = N;
+        // (2) area and int |grad q|^2 dA in one pass over q (per-CTA partials only)
+        ScanOut so; so.p[0] = so.p[1] = so.p[2] = so.p[3] = nullptr; so.stride = N;
         const void* integs[1] = { stencil ? nullptr : (const void*)((const char*)a->grdS + (size_t)s0 * P * gsz) };
         const int integ_dt[1] = { a->grdS_dtype };
+        HistOnly ho;
         if (bin_accumulate_impl(q, a->q_dtype, ns, P, edges, N + 1, N, 0, a->dA, a->dA_dtype, 1,
                                 integs, integ_dt, stencil ? 0 : 1, nullptr,
                                 a->lt ? XC_SCAN_PREFIX : XC_SCAN_TOTAL_MINUS, decr,
                                 nullptr, so, nullptr, w_hist, pl.ws_hist, stream,
-                                stencil ? &sa : nullptr)) return 1;
+                                stencil ? &sa : nullptr, &ho)) return 1;
         mark(3);
-        // (3) latEq = Table.lookup_coordinates(area)
-        if (xc_interp(area, N, N, a->table, 0, a->table_coord, 0, a->n_table, -1, ns, latEq, stream)) return 1;
-        // (5)/(4) Lmin, d/dA, Leq2, nkeff
-        if (xc_lmin(latEq, ns * (long)N, Lmin, stream)) return 1;
-        if (xc_gradient_wrt_area(intg, XC_F64, area, XC_F64, ns, N, dint, stream)) return 1;
-        if (xc_gradient_wrt_area(ctr, a->ctr_dtype == XC_F32 ? XC_F32_AS_F64 : XC_F64, area, XC_F64,
-                                 ns, N, dq, stream)) return 1;
-        if (xc_leq2(dint, dq, ns * (long)N, Leq2, stream)) return 1;
-        if (xc_nkeff(Leq2, Lmin, a->keff_mask, ns * (long)N, nk, stream)) return 1;
-        // (3) Q(eq_coord) = interp_to_coords(eq_coord, latEq, ctr)
-        if (xc_interp(a->eq_coord, 0, ny, latEq, N, ctr, N, N, -1, ns, Qref, stream)) return 1;
+        // scan + (3) latEq + (5)/(4) Lmin, d/dA, Leq2, nkeff + (3) Q(eq_coord), one launch
+        if (scan_epilogue(ho.part, ho.C, ns, N, a->lt, decr, ctr, a->ctr_dtype == XC_F32,
+                          a->table, a->table_coord, a->n_table, a->eq_coord, ny, a->keff_mask, a->increase,
+                          area, intg, latEq, Lmin, dint, dq, Leq2, nk, Qref, sorted, any_unsorted, stream)) return 1;
         mark(4);
         // (6) LWA
         if (a->lwa)
-            if (xc_lwa(q, a->q_dtype, ns, ny, nx, Qref, a->ww, a->increase, a->part, 1,
-                       a->lwa + (size_t)s0 * P, w_lwa, pl.ws_lwa, stream)) return 1;
+            if (lwa_impl(q, a->q_dtype, ns, ny, nx, Qref, a->ww, a->increase, a->part, 1,
+                         a->lwa + (size_t)s0 * P, sorted, any_unsorted, true, stream)) return 1;
         mark(5);
         ++pass;
     }

@@ -477,7 +477,7 @@ int xc::bin_accumulate_impl(const void* q, int q_dtype, long S, long P,
                             int scan_mode, const int32_t* decreasing,
                             double* pdf, const ScanOut& so, int32_t* bin_idx,
                             void* workspace, size_t ws_bytes, void* stream,
-                            const StencilArgs* stencil)
+                            const StencilArgs* stencil, HistOnly* hist_only)
 {
     XC_REQUIRE(q && edges && dA, "xc_bin_accumulate: null pointer");
     XC_REQUIRE(S > 0 && P > 0 && N >= 1, "xc_bin_accumulate: need S>0, P>0, N>=1");
@@ -524,6 +524,7 @@ int xc::bin_accumulate_impl(const void* q, int q_dtype, long S, long P,
         }
         if (rc) return rc;
     }
+    if (hist_only) { hist_only->part = hp.part; hist_only->C = pl.C; return 0; }
     XC_REQUIRE(S <= 0x7fffffffL, "xc_bin_accumulate: too many slices");
     dim3 g2((unsigned)S, (unsigned)K);
     XC_REQUIRE((size_t)N * 8 <= 200 * 1024, "xc_bin_accumulate: N too large for the scan kernel");

@@ -14,6 +14,7 @@ struct ScanOut { double* p[4]; long stride; };
 struct StencilArgs { int ny, nx; const double* cx; const double* cy; };
 int row_metrics(const double* lat_rad, int ny, double dlambda, double* cx, double* cy, void* stream);
 
+struct HistOnly;
 int bin_accumulate_impl(const void* q, int q_dtype, long S, long P,
                         const double* edges, long edges_stride, int N,
                         int closed_right,
@@ -23,6 +24,28 @@ int bin_accumulate_impl(const void* q, int q_dtype, long S, long P,
                         int scan_mode, const int32_t* decreasing,
                         double* pdf, const ScanOut& so, int32_t* bin_idx,
                         void* workspace, size_t ws_bytes, void* stream,
-                        const StencilArgs* stencil = nullptr);
+                        const StencilArgs* stencil = nullptr, struct HistOnly* hist_only = nullptr);
+
+// when passed to bin_accumulate_impl the scan kernel is skipped and the caller
+// gets the per-CTA partials [S][C][K][N] (the fused epilogue reduces them itself)
+struct HistOnly { const double* part; int C; };
+
+int scan_epilogue(const double* part, int C, long S, int N, int lt, const int32_t* decreasing,
+                  const double* ctr, int ctr_f32,
+                  const double* table, const double* table_coord, int n_table,
+                  const double* eq_coord, int ny, double keff_mask, int increase,
+                  double* area, double* intg, double* latEq, double* Lmin, double* dint,
+                  double* dq, double* Leq2, double* nkeff, double* Qref,
+                  int32_t* sorted, int32_t* any_unsorted, void* stream);
+
+// levels (+ optional per-'time'-branch edges in the same launch); clears *flag_to_clear
+int minmax_levels_impl(const void* q, int q_dtype, long S, long P, int N, int increase, int out_dtype,
+                       double* levels, double* minmax, double* edges, int32_t* decreasing,
+                       int32_t* flag_to_clear, void* workspace, size_t ws_bytes, void* stream);
+
+// LWA with sortedness flags already on the device (fused path)
+int lwa_impl(const void* q, int q_dtype, long S, int n_eq, int n_x, const double* Qref, const double* ww,
+             int increase, int part, int variant, double* out, int32_t* sorted,
+             const int32_t* any_unsorted, bool flags_ready, void* stream);
 
 }  // namespace xc

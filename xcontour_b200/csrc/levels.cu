@@ -6,6 +6,7 @@
 // per thread, one (min,max) pair per CTA written as a partial so the result is
 // order-independent and needs no atomics.
 #include "common.cuh"
+#include "internal.h"
 #include <math_constants.h>
 
 namespace xc {
@@ -88,9 +89,12 @@ k_minmax_partial(const T* __restrict__ q, long P, long per, double* __restrict__
 // a final cast to the requested contour dtype (core.py:228-246).
 __global__ void k_levels(const double* __restrict__ part, int C, int N, int increase,
                          int q_is_f32, int out_is_f32,
-                         double* __restrict__ levels, double* __restrict__ minmax)
+                         double* __restrict__ levels, double* __restrict__ minmax,
+                         double* __restrict__ edges, int32_t* __restrict__ decreasing,
+                         int32_t* __restrict__ flag_to_clear)
 {
     const long s = blockIdx.x;
+    if (flag_to_clear && s == 0 && threadIdx.x == 0) *flag_to_clear = 0;
     __shared__ double sh[2];
     if (threadIdx.x < 32) {
         double mn = CUDART_INF, mx = -CUDART_INF;
@@ -116,6 +120,24 @@ __global__ void k_levels(const double* __restrict__ part, int C, int N, int incr
         double v = __dadd_rn(__dmul_rn(steps, (double)k), start);
         if (out_is_f32) v = (double)__double2float_rn(v);
         levels[s * N + k] = v;
+    }
+    if (edges) {            // per-'time' branch edges (core.py:1273-1281), same rules as k_hist_edges
+        auto level = [&](int k) {
+            double v = __dadd_rn(__dmul_rn(steps, (double)k), start);
+            return out_is_f32 ? (double)__double2float_rn(v) : v;
+        };
+        const double c0 = level(0), cl = level(N - 1);
+        const bool binc = c0 < cl;
+        const double first = binc ? c0 : cl, last = binc ? cl : c0;
+        const double d = out_is_f32 ? (double)__fsub_rn((float)last, (float)first) : __dsub_rn(last, first);
+        const double step = __ddiv_rn(d, (double)(N - 1));
+        double* e = edges + s * (long)(N + 1);
+        for (int k = threadIdx.x; k <= N; k += blockDim.x) {
+            double v = (k == 0) ? __dsub_rn(first, step) : (binc ? level(k - 1) : level(N - k));
+            if (k == N) v = __dadd_rn(v, 1e-8);
+            e[k] = v;
+        }
+        if (threadIdx.x == 0 && decreasing) decreasing[s] = binc ? 0 : 1;
     }
 }
 
@@ -178,6 +200,14 @@ extern "C" int xc_minmax_levels(const void* q, int q_dtype, long S, long P,
                                 double* levels, double* minmax,
                                 void* workspace, size_t ws_bytes, void* stream)
 {
+    return minmax_levels_impl(q, q_dtype, S, P, N, increase, out_dtype, levels, minmax,
+                              nullptr, nullptr, nullptr, workspace, ws_bytes, stream);
+}
+
+int xc::minmax_levels_impl(const void* q, int q_dtype, long S, long P, int N, int increase, int out_dtype,
+                           double* levels, double* minmax, double* edges, int32_t* decreasing,
+                           int32_t* flag_to_clear, void* workspace, size_t ws_bytes, void* stream)
+{
     XC_REQUIRE(q && levels, "xc_minmax_levels: null pointer");
     XC_REQUIRE(S > 0 && P > 0 && N >= 2, "xc_minmax_levels: need S>0, P>0, N>=2");
     XC_REQUIRE(q_dtype == XC_F32 || q_dtype == XC_F64, "xc_minmax_levels: bad dtype");
@@ -200,7 +230,7 @@ extern "C" int xc_minmax_levels(const void* q, int q_dtype, long S, long P,
         XC_LAUNCH_OK();
     }
     k_levels<<<(unsigned)S, 128, 0, st>>>(part, (int)C, N, increase, q_dtype == XC_F32,
-                                          out_dtype == XC_F32, levels, minmax);
+                                          out_dtype == XC_F32, levels, minmax, edges, decreasing, flag_to_clear);
     XC_LAUNCH_OK();
     return 0;
 }

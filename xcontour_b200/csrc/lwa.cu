@@ -16,6 +16,7 @@
 // warp-private scatter resolved with the same byte-tag protocol as hist.cu.
 // Profiles that are not sorted (or contain NaN) take the exact O(n_eq^2) kernel.
 #include "common.cuh"
+#include "internal.h"
 #include <math_constants.h>
 #include <stdlib.h>
 
@@ -283,8 +284,9 @@ __global__ void __launch_bounds__(256)
 k_lwa_brute(const QT* __restrict__ q, long S, int ny, int nx,
             const double* __restrict__ Qref, const double* __restrict__ ww,
             int increase, int part, int variant, const int32_t* __restrict__ skip,
-            double* __restrict__ out)
+            const int32_t* __restrict__ gate, double* __restrict__ out)
 {
+    if (gate && *gate == 0) return;            // every slice went down the fast path
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int tiles_x = (nx + 31) / 32, tiles_y = (ny + 7) / 8;
     const long tiles = (long)tiles_x * tiles_y;
@@ -432,23 +434,33 @@ extern "C" int xc_lwa(const void* q, int q_dtype, long S, int n_eq, int n_x,
                       int increase, int part, int variant,
                       double* out, void* workspace, size_t ws_bytes, void* stream)
 {
+    XC_REQUIRE(workspace && ws_bytes >= xc_lwa_workspace_bytes(S), "xc_lwa: workspace too small");
+    Arena ar(workspace, ws_bytes);
+    int32_t* sorted = ar.take<int32_t>((size_t)S);
+    return lwa_impl(q, q_dtype, S, n_eq, n_x, Qref, ww, increase, part, variant, out, sorted,
+                    nullptr, false, stream);
+}
+
+int xc::lwa_impl(const void* q, int q_dtype, long S, int n_eq, int n_x, const double* Qref, const double* ww,
+                 int increase, int part, int variant, double* out, int32_t* sorted,
+                 const int32_t* any_unsorted, bool flags_ready, void* stream)
+{
     XC_REQUIRE(q && Qref && ww && out, "xc_lwa: null pointer");
     XC_REQUIRE(S > 0 && n_eq >= 1 && n_x >= 1, "xc_lwa: need S>0, n_eq>=1, n_x>=1");
     XC_REQUIRE(q_dtype == XC_F32 || q_dtype == XC_F64, "xc_lwa: bad dtype");
     XC_REQUIRE(part >= XC_PART_ALL && part <= XC_PART_LOWER,
                "invalid part, should be in ['all', 'upper', 'lower']");
     XC_REQUIRE(variant == 1 || variant == 2, "xc_lwa: variant must be 1 or 2");
-    XC_REQUIRE(workspace && ws_bytes >= xc_lwa_workspace_bytes(S), "xc_lwa: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
-    Arena ar(workspace, ws_bytes);
-    int32_t* sorted = ar.take<int32_t>((size_t)S);
     const bool match = lwa_use_match();
     const int qbytes = q_dtype == XC_F32 ? 4 : 8;
     const int tc = (n_eq < 65535) ? lwa_pick_tc(n_eq, qbytes, !match) : 0;
     const bool fast = (variant == 1) && tc >= 1;
     if (fast) {
-        k_check_sorted<<<(unsigned)S, 256, 0, st>>>(Qref, n_eq, increase, sorted);
-        XC_LAUNCH_OK();
+        if (!flags_ready) {
+            k_check_sorted<<<(unsigned)S, 256, 0, st>>>(Qref, n_eq, increase, sorted);
+            XC_LAUNCH_OK();
+        }
         int rc;
         if (q_dtype == XC_F32)
             rc = match ? launch_lwa_fast<float, true>((const float*)q, S, n_eq, n_x, Qref, ww, increase, part, sorted, out, tc, st)
@@ -458,15 +470,17 @@ extern "C" int xc_lwa(const void* q, int q_dtype, long S, int n_eq, int n_x,
                        : launch_lwa_fast<double, false>((const double*)q, S, n_eq, n_x, Qref, ww, increase, part, sorted, out, tc, st);
         if (rc) return rc;
     }
-    // exact loop for whatever the fast path did not take
+    // exact loop for whatever the fast path did not take (exits at once when the
+    // fused epilogue reported that every profile is sorted)
     dim3 blk(32, 8);
-    unsigned nb = (unsigned)(sm_count() * 8);
+    const bool gated = fast && flags_ready && any_unsorted;
+    unsigned nb = (unsigned)(sm_count() * (gated ? 1 : 8));
     if (q_dtype == XC_F32)
         k_lwa_brute<float><<<nb, blk, 0, st>>>((const float*)q, S, n_eq, n_x, Qref, ww, increase, part,
-                                               variant, fast ? sorted : nullptr, out);
+                                               variant, fast ? sorted : nullptr, gated ? any_unsorted : nullptr, out);
     else
         k_lwa_brute<double><<<nb, blk, 0, st>>>((const double*)q, S, n_eq, n_x, Qref, ww, increase, part,
-                                                variant, fast ? sorted : nullptr, out);
+                                                variant, fast ? sorted : nullptr, gated ? any_unsorted : nullptr, out);
     XC_LAUNCH_OK();
     return 0;
 }
