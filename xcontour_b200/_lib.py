@@ -11,7 +11,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_double, c_int, c_int32,
                     c_long, c_size_t, c_void_p)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libxcb200.so")
+LIB_PATH = os.environ.get("XCB200_LIB") or os.path.join(HERE, "libxcb200.so")   # XCB200_LIB: A/B builds only
 
 XC_F32, XC_F64, XC_F32_AS_F64 = 0, 1, 2
 SCAN_PREFIX, SCAN_TOTAL_MINUS, SCAN_SUFFIX = 0, 1, 2

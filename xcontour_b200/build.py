@@ -25,15 +25,19 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
+def build(force=False, verbose=False, variant=None, defines=()):
+    """variant/defines: build an experimental libxcb200_<variant>.so with extra -D
+    flags (selected at run time with XCB200_LIB=<path>); used for A/B timing only."""
+    lib = LIB if variant is None else os.path.join(HERE, "libxcb200_%s.so" % variant)
+    if variant is None and not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
     objs = []
     procs = []
+    suffix = ".o" if variant is None else ".%s.o" % variant
     for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(CSRC, src.replace(".cu", suffix))
+        cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     failed = False
@@ -44,15 +48,15 @@ def build(force=False, verbose=False):
         if p.returncode != 0:
             failed = True
             sys.stderr.write("nvcc failed on %s:\n%s\n" % (src, out))
-    with open(os.path.join(CSRC, "build.log"), "w") as f:
+    with open(os.path.join(CSRC, "build.log" if variant is None else "build.%s.log" % variant), "w") as f:
         f.write("\n".join(log))
     if failed:
         raise RuntimeError("libxcb200 build failed")
     if verbose:
         print("\n".join(log))
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nvcc, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
     subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

@@ -41,8 +41,29 @@ __global__ void k_check_sorted(const double* __restrict__ Q, int ny, int increas
     if (threadIdx.x == 0) flag[s] = bad ? 0 : 1;
 }
 
-constexpr int LWA_BIG = 128;      // rows staged per block (4 warp-steps of 32 rows)
-constexpr int LWA_RS  = 130;      // staging row stride; == 2 (mod 32) keeps the transposed store conflict-free
+// Rows are staged in blocks of LWA_BIG = 32*LWA_NI.  Inside a block lane l works
+// on rows {NI*l + u : u < NI}: an odd stride between the lanes of one item set
+// keeps the 128-bit accesses to the difference array bank-conflict free and
+// makes two lanes of a set share a far-end slot less often than adjacent rows do.
+#ifndef XC_LWA_NI
+#define XC_LWA_NI 3
+#endif
+#ifndef XC_LWA_MAP           /* 1: lane l owns rows NI*l+u of a block; 0: rows 32*u+l */
+#define XC_LWA_MAP 1
+#endif
+#ifndef XC_LWA_UPFRONT       /* 1: all MATCH.ANY of a step issued before the peel loops */
+#define XC_LWA_UPFRONT 0
+#endif
+#ifndef XC_LWA_MINB          /* min blocks per SM given to __launch_bounds__ (0 = unspecified) */
+#define XC_LWA_MINB 0
+#endif
+#ifndef XC_LWA_BISECT        /* unrolled branch-free bisection steps before the fallback loop */
+#define XC_LWA_BISECT 0
+#endif
+constexpr int LWA_NI  = XC_LWA_NI;
+constexpr int LWA_BIG = 32 * LWA_NI;       // rows per staged block
+constexpr int LWA_RSW = LWA_BIG + 2;       // staging row stride of ww (doubles)
+constexpr int LWA_RSQ = LWA_BIG + 4;       // staging row stride of q
 
 struct LwaSmem {
     size_t off_Q, off_D, off_lut, off_tag, off_sq, off_sw, total;
@@ -56,64 +77,68 @@ static __host__ __device__ inline LwaSmem lwa_layout(int ny, int TC, int qbytes,
     size_t o = 0;
     L.off_Q = o;   o += (size_t)((ny + 1) & ~1) * 8;
     L.off_D = o;   o += (size_t)TC * L.nyp * 16;
-    L.off_sw = o;  o += (size_t)TC * LWA_RS * 8;
-    L.off_sq = o;  o += (size_t)TC * LWA_RS * qbytes;
+    L.off_sw = o;  o += (size_t)TC * LWA_RSW * 8;
+    L.off_sq = o;  o += (size_t)TC * LWA_RSQ * qbytes;
     o = (o + 15) & ~(size_t)15;
-    L.off_lut = o; o += (size_t)(LWA_LUT + 2) * 2;
+    L.off_lut = o; o += (size_t)(LWA_LUT + 1) * 4;
     o = (o + 15) & ~(size_t)15;
     L.off_tag = o; if (tags) o += (size_t)TC * L.tagp;
     L.total = o;
     return L;
 }
 
-__device__ __forceinline__ int lwa_bucket(double v, double qmin, double scale)
+// fp32 bucket of a value; monotone in its argument, so bucket(Q_j) < bucket(v)
+// implies Q_j < v (and > implies >): the LUT only narrows the range, the exact
+// fp64 comparisons against Q decide.
+__device__ __forceinline__ int lwa_bucket(float vf, float qminf, float scalef)
 {
-    double t = (v - qmin) * scale;
-    int b = (int)fmin(t, (double)(LWA_LUT - 1));
-    return b < 0 ? 0 : b;
+    const float t = fminf(fmaxf((vf - qminf) * scalef, 0.0f), (float)(LWA_LUT - 1));
+    return __float2int_rz(t);
 }
 
-// Warp-private scatter-add of -(w, wv) into Dw[target] for the lanes with
-// act == true; lanes that share a target are serialised.
-//   MATCH: one MATCH.ANY gives every lane the mask of its peers; the lowest
-//          remaining peer of each group does a plain read-modify-write per
-//          round, every member then clears that bit.
-//   tags : every pending lane writes its id into a byte tag of the target, the
-//          lane that reads its own id back owns the slot for this round.
+// Warp-private scatter-add of (nw, nwv) into Dw[target] for NI items per lane;
+// lanes of one item set that share a target are serialised (MATCH.ANY peel or
+// byte tags, see hist.cu).
 template <bool MATCH>
-__device__ __forceinline__ void lwa_scatter_sub4(double2* Dw, uint8_t* tagw, const int (&target)[4],
-                                                 const double (&w)[4], const double (&wv)[4],
-                                                 const bool (&act)[4], int lane)
+__device__ __forceinline__ void lwa_scatter(double2* Dw, uint8_t* tagw, const int (&target)[LWA_NI],
+                                            const double (&nw)[LWA_NI], const double (&nwv)[LWA_NI],
+                                            const bool (&act)[LWA_NI], int lane)
 {
     if (MATCH) {
-        unsigned peers[4];
+#if XC_LWA_UPFRONT
+        unsigned peers[LWA_NI];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < LWA_NI; ++u) {
             peers[u] = __match_any_sync(XC_FULL, act[u] ? (unsigned)target[u] : (0x80000000u | (unsigned)lane));
             if (!act[u]) peers[u] = 0u;
         }
-        unsigned more;
-        do {
+#endif
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (peers[u] && (__ffs(peers[u]) - 1) == lane) {
-                    double2 t = Dw[target[u]]; t.x -= w[u]; t.y -= wv[u]; Dw[target[u]] = t;
+        for (int u = 0; u < LWA_NI; ++u) {
+#if XC_LWA_UPFRONT
+            unsigned pr = peers[u];
+#else
+            unsigned pr = __match_any_sync(XC_FULL, act[u] ? (unsigned)target[u] : (0x80000000u | (unsigned)lane));
+            if (!act[u]) pr = 0u;
+#endif
+            do {
+                if (pr && (__ffs(pr) - 1) == lane) {
+                    double2 t = Dw[target[u]]; t.x += nw[u]; t.y += nwv[u]; Dw[target[u]] = t;
                 }
-                peers[u] &= peers[u] - 1u;
+                pr &= pr - 1u;
                 __syncwarp();
-            }
-            more = peers[0] | peers[1] | peers[2] | peers[3];
-        } while (__any_sync(XC_FULL, more != 0u));
+            } while (__any_sync(XC_FULL, pr != 0u));
+        }
     } else {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < LWA_NI; ++u) {
             bool a = act[u];
             unsigned pending = __ballot_sync(XC_FULL, a);
             while (pending) {
                 if (a) tagw[target[u]] = (uint8_t)lane;
                 __syncwarp();
                 if (a && tagw[target[u]] == (uint8_t)lane) {
-                    double2 t = Dw[target[u]]; t.x -= w[u]; t.y -= wv[u]; Dw[target[u]] = t;
+                    double2 t = Dw[target[u]]; t.x += nw[u]; t.y += nwv[u]; Dw[target[u]] = t;
                     a = false;
                 }
                 __syncwarp();
@@ -124,8 +149,19 @@ __device__ __forceinline__ void lwa_scatter_sub4(double2* Dw, uint8_t* tagw, con
 }
 
 // grid = (ceil(nx/TC), nslices), block = TC warps; warp w owns column i0 + w.
+#if XC_LWA_MINB > 0
+#define XC_LWA_BOUNDS __launch_bounds__(LWA_MAX_TC * 32, XC_LWA_MINB)
+#else
+#define XC_LWA_BOUNDS __launch_bounds__(LWA_MAX_TC * 32)
+#endif
+#if XC_LWA_MAP
+#define LWA_ROW(lane, u) (LWA_NI * (lane) + (u))
+#else
+#define LWA_ROW(lane, u) (32 * (u) + (lane))
+#endif
+
 template <typename QT, bool MATCH>
-__global__ void __launch_bounds__(LWA_MAX_TC * 32)
+__global__ void XC_LWA_BOUNDS
 k_lwa_fast(const QT* __restrict__ q, long s0, int ny, int nx,
            const double* __restrict__ Qref, const double* __restrict__ ww,
            int increase, int part, const int32_t* __restrict__ sorted,
@@ -137,9 +173,9 @@ k_lwa_fast(const QT* __restrict__ q, long s0, int ny, int nx,
     const LwaSmem L = lwa_layout(ny, TC, (int)sizeof(QT), !MATCH);
     double*   Qs  = reinterpret_cast<double*>(smem + L.off_Q);
     double2*  D   = reinterpret_cast<double2*>(smem + L.off_D);
-    double*   sw  = reinterpret_cast<double*>(smem + L.off_sw);    // [TC][LWA_RS]
-    QT*       sq  = reinterpret_cast<QT*>(smem + L.off_sq);        // [TC][LWA_RS]
-    uint16_t* lut = reinterpret_cast<uint16_t*>(smem + L.off_lut);
+    double*   sw  = reinterpret_cast<double*>(smem + L.off_sw);    // [TC][LWA_RSW]
+    QT*       sq  = reinterpret_cast<QT*>(smem + L.off_sq);        // [TC][LWA_RSQ]
+    uint32_t* lut = reinterpret_cast<uint32_t*>(smem + L.off_lut); // lut[b] | lut[b+1] << 16
     uint8_t*  tag = smem + L.off_tag;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
@@ -148,35 +184,46 @@ k_lwa_fast(const QT* __restrict__ q, long s0, int ny, int nx,
     const QT* qs = q + s * (long)ny * nx;
     const double* Qg = Qref + s * (long)ny;
 
-    // staging map: element e = k*nthr + tid of a 128 x TC block -> (row, col);
-    // nthr = 32*TC, so row = 32*k + tid/TC and col = tid%TC for every k
+    // staging map: element k*nthr + tid of a BIG x TC block -> row 32*k + tid/TC,
+    // col tid%TC (nthr = 32*TC): a warp reads 32/TC... rows of TC contiguous values
     const int rr = tid / TC, cc = tid - rr * TC;
     const bool col_ok = (i0 + cc) < nx;
-    QT pq[4]; double pw[4];
+    const QT*     gq = qs + (long)rr * nx + i0 + cc;               // element (row rr, col cc) of block 0
+    const double* gw = ww + (long)rr * nx + i0 + cc;
+    const long    gstep = 32L * nx;
+    QT pq[LWA_NI]; double pw[LWA_NI];
     auto fetch = [&](int b) {
+        const QT* a = gq + (long)b * LWA_NI * gstep;
+        const double* c = gw + (long)b * LWA_NI * gstep;
+        const int jb = b * LWA_BIG + rr;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int j = b * LWA_BIG + 32 * k + rr;
-            if (j < ny && col_ok) {
-                pq[k] = __ldg(qs + (long)j * nx + i0 + cc);
-                pw[k] = __ldg(ww + (long)j * nx + i0 + cc);
-            } else { pq[k] = (QT)CUDART_NAN; pw[k] = 0.0; }
+        for (int k = 0; k < LWA_NI; ++k) {
+            if (jb + 32 * k < ny && col_ok) { pq[k] = __ldg(a + k * gstep); pw[k] = __ldg(c + k * gstep); }
+            else { pq[k] = (QT)CUDART_NAN; pw[k] = 0.0; }
         }
     };
     fetch(0);
 
     for (int j = tid; j < ny; j += nthr) Qs[j] = sg * Qg[j];
-    for (int k = tid; k < TC * L.nyp; k += nthr) D[k] = make_double2(0.0, 0.0);
     __syncthreads();
     const double qmin = Qs[0], qmax = Qs[ny - 1];
-    const double scale = (qmax > qmin) ? (double)LWA_LUT / (qmax - qmin) : 0.0;
-    // lut[b] = first j whose bucket is >= b; buckets are monotone in Q
-    for (int j = tid; j <= ny; j += nthr) {
-        int bj = (j < ny) ? lwa_bucket(Qs[j], qmin, scale) : LWA_LUT;
-        int bp = (j > 0) ? lwa_bucket(Qs[j - 1], qmin, scale) : -1;
-        for (int b = bp + 1; b <= bj; ++b) lut[b] = (uint16_t)j;
+    const float qminf = (float)qmin;
+    const float scalef = (qmax > qmin) ? (float)((double)LWA_LUT / (qmax - qmin)) : 0.0f;
+    // first j whose bucket is >= b, for b = 0..LWA_LUT (buckets are monotone in Q);
+    // entry b of the packed table holds (first[b], first[b+1])
+    {
+        uint16_t* first = reinterpret_cast<uint16_t*>(D);           // D is zeroed right after
+        for (int j = tid; j <= ny; j += nthr) {
+            int bj = (j < ny) ? lwa_bucket((float)Qs[j], qminf, scalef) : LWA_LUT;
+            int bp = (j > 0) ? lwa_bucket((float)Qs[j - 1], qminf, scalef) : -1;
+            for (int b = bp + 1; b <= bj; ++b) first[b] = (uint16_t)j;
+        }
+        __syncthreads();
+        for (int b = tid; b < LWA_LUT; b += nthr) lut[b] = (uint32_t)first[b] | ((uint32_t)first[b + 1] << 16);
+        __syncthreads();
+        for (int k = tid; k < TC * L.nyp; k += nthr) D[k] = make_double2(0.0, 0.0);
+        // (the sync after the first staging store below also covers D)
     }
-    // (the sync after the first staging store below also covers the lut)
 
     // which mask regions are integrated (core.py:773-784)
     const bool keep_pos = (part == XC_PART_UPPER) == (increase != 0);
@@ -185,66 +232,63 @@ k_lwa_fast(const QT* __restrict__ q, long s0, int ny, int nx,
 
     double2* Dw = D + (size_t)warp * L.nyp;
     uint8_t* tagw = tag + (size_t)warp * L.tagp;
-    const QT*     sqw = sq + (size_t)warp * LWA_RS;
-    const double* sww = sw + (size_t)warp * LWA_RS;
+    const QT*     sqw = sq + (size_t)warp * LWA_RSQ;
+    const double* sww = sw + (size_t)warp * LWA_RSW;
     const int nblk = (ny + LWA_BIG - 1) / LWA_BIG;
 
     for (int b = 0; b < nblk; ++b) {
         if (b > 0) __syncthreads();                          // everyone is done with the staging buffers
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {                        // transposed store: [col][row]
-            sq[cc * LWA_RS + 32 * k + rr] = pq[k];
-            sw[cc * LWA_RS + 32 * k + rr] = pw[k];
+        for (int k = 0; k < LWA_NI; ++k) {                   // transposed store: [col][row]
+            sq[cc * LWA_RSQ + 32 * k + rr] = pq[k];
+            sw[cc * LWA_RSW + 32 * k + rr] = pw[k];
         }
         __syncthreads();
         if (b + 1 < nblk) fetch(b + 1);                      // next block's loads fly during the work below
 
-        int    tgt[4]; bool act[4]; double wq[4], wvq[4];
+        const int jblk = b * LWA_BIG;
+        int tgt[LWA_NI]; bool act[LWA_NI]; double nw[LWA_NI], nwv[LWA_NI];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int jp = b * LWA_BIG + 32 * u + lane;
-            const double v = sg * (double)sqw[32 * u + lane];
-            const double w = sww[32 * u + lane];
-            bool a = (jp < ny) && !isnan(v) && !isnan(w);
+        for (int u = 0; u < LWA_NI; ++u) {
+            const int jp = jblk + LWA_ROW(lane, u);
+            const QT qraw = sqw[LWA_ROW(lane, u)];
+            const double v = sg * (double)qraw;
+            const double w = sww[LWA_ROW(lane, u)];
+            bool a = (jp < ny) && (v == v);
             int target = 0;
-            if (a) {
-                int lo;
-                if (v < qmin) lo = 0;
-                else if (v > qmax) lo = ny;
-                else {
-                    const int bk = lwa_bucket(v, qmin, scale);
-                    int x = lut[bk], e = lut[bk + 1];
+            {
+                const uint32_t pk = lut[lwa_bucket((float)v, qminf, scalef)];
+                int x = (int)(pk & 0xffffu), e = (int)(pk >> 16);
 #pragma unroll
-                    for (int it = 0; it < 3; ++it) {         // branch-free bisection: covers e - x <= 7
-                        const int mid = (x + e) >> 1;
-                        const bool open = x < e;
-                        const bool below = open && (Qs[open ? mid : 0] < v);
-                        x = below ? mid + 1 : x;
-                        e = (open && !below) ? mid : e;
-                    }
-                    while (x < e) {                          // first idx with Qs >= v
-                        int mid = (x + e) >> 1;
-                        if (Qs[mid] < v) x = mid + 1; else e = mid;
-                    }
-                    lo = x;
+                for (int it = 0; it < XC_LWA_BISECT; ++it) { // branch-free bisection: 3 steps cover e - x <= 7
+                    const int mid = (x + e) >> 1;
+                    const bool open = x < e;
+                    const bool below = open && (Qs[open ? mid : 0] < v);
+                    x = below ? mid + 1 : x;
+                    e = (open && !below) ? mid : e;
                 }
-                if (lo > jp + 1) { target = lo; a = use_t1; }
+                while (x < e) {                              // wide buckets (flat stretches of Q)
+                    const int mid = (x + e) >> 1;
+                    if (Qs[mid] < v) x = mid + 1; else e = mid;
+                }
+                const int lo = x;                            // #{Q < v}
+                if (lo > jp + 1) { target = lo; a = a && use_t1; }
                 else {
-                    int hi = lo;
+                    int hi = lo;                             // #{Q <= v}
                     while (hi < ny && Qs[hi] == v) ++hi;
-                    if (hi <= jp) { target = hi; a = use_t2; }
-                    else a = false;
+                    target = hi;
+                    a = a && (hi <= jp) && use_t2;
                 }
             }
-            tgt[u] = target; act[u] = a; wq[u] = w; wvq[u] = w * v;
+            tgt[u] = target; act[u] = a; nw[u] = -w; nwv[u] = -(w * v);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {                        // own slot j'+1: +(w, w v), no conflicts
-            const int jp = b * LWA_BIG + 32 * u + lane;
-            if (act[u]) { double2 t = Dw[jp + 1]; t.x += wq[u]; t.y += wvq[u]; Dw[jp + 1] = t; }
+        for (int u = 0; u < LWA_NI; ++u) {                   // own slot j'+1: +(w, w v), no conflicts
+            const int jo = jblk + LWA_ROW(lane, u) + 1;
+            if (act[u]) { double2 t = Dw[jo]; t.x -= nw[u]; t.y -= nwv[u]; Dw[jo] = t; }
         }
         __syncwarp();
-        lwa_scatter_sub4<MATCH>(Dw, tagw, tgt, wq, wvq, act, lane);   // far end of the range: -(w, w v)
+        lwa_scatter<MATCH>(Dw, tagw, tgt, nw, nwv, act, lane);   // far end of the range: -(w, w v)
     }
 
     // prefix sums down the column: each lane owns a contiguous run of rows (odd
@@ -271,8 +315,8 @@ k_lwa_fast(const QT* __restrict__ q, long s0, int ny, int nx,
     __syncthreads();
     if (col_ok) {
         const double2* Dc = D + (size_t)cc * L.nyp;
-        for (int j = rr; j < ny; j += 32)
-            out[(s * ny + j) * (long)nx + i0 + cc] = Dc[j].x;
+        double* o = out + (s * ny + rr) * (long)nx + i0 + cc;
+        for (int j = rr; j < ny; j += 32, o += gstep) *o = Dc[j].x;
     }
 }
 
@@ -383,7 +427,8 @@ using namespace xc;
 static bool lwa_use_match()
 {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("XCB200_LWA_DEDUP"); v = (e && e[0] == 't') ? 0 : 1; }
+    // measured on B200 (scripts/ab_variants.sh): the byte-tag protocol is ~10 % faster here
+    if (v < 0) { const char* e = getenv("XCB200_LWA_DEDUP"); v = (e && e[0] == 'm') ? 1 : 0; }
     return v == 1;
 }
 
@@ -455,7 +500,7 @@ int xc::lwa_impl(const void* q, int q_dtype, long S, int n_eq, int n_x, const do
     const bool match = lwa_use_match();
     const int qbytes = q_dtype == XC_F32 ? 4 : 8;
     const int tc = (n_eq < 65535) ? lwa_pick_tc(n_eq, qbytes, !match) : 0;
-    const bool fast = (variant == 1) && tc >= 1;
+    const bool fast = (variant == 1) && tc >= 1 && (size_t)tc * (n_eq + 2) * 16 >= (size_t)(LWA_LUT + 1) * 2;
     if (fast) {
         if (!flags_ready) {
             k_check_sorted<<<(unsigned)S, 256, 0, st>>>(Qref, n_eq, increase, sorted);
