@@ -1,5 +1,3 @@
 for v in "$@"; do
-  for d in m t; do
-    XCB200_LWA_DEDUP=$d XCB200_HIST_DEDUP=$d XCB200_LIB=$PWD/xcontour_b200/libxcb200_$v.so python scripts/time_stages.py 32 16 2>&1 | tail -1 | sed "s/^/[$d] /"
-  done
+    XCB200_LIB=$PWD/xcontour_b200/libxcb200_$v.so python scripts/time_stages.py 32 16 2>&1 | tail -1
 done

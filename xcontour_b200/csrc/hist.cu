@@ -511,6 +511,14 @@ int xc::bin_accumulate_impl(const void* q, int q_dtype, long S, long P,
     hp.part = ar.take<double>((size_t)S * pl.C * K * N);
     hp.bin_idx = bin_idx;
     hp.ncopy = pl.ncopy;
+    // the fused Keff pass (fp32 tracer and areas, {dA, |grad q|^2 dA}, uniform per-slice
+    // edges, no mask / bin output) has a dedicated lean kernel
+    if (hist_only && stencil && acc_area && n_int == 0 && !q_mask && !bin_idx && !closed_right &&
+        edges_stride == N + 1 && pl.priv) {
+        const int r = hist_keff_try(q, q_dtype, S, P, edges, N, dA, dA_dtype, stencil, pl.C, hp.part, stream);
+        if (r == 2) return 1;
+        if (r == 0) { hist_only->part = hp.part; hist_only->C = pl.C; return 0; }
+    }
     for (long s0 = 0; s0 < S; s0 += 65535) {
         long ns = S - s0 < 65535 ? S - s0 : 65535;
         hp.s0 = s0;

@@ -38,6 +38,11 @@ int scan_epilogue(const double* part, int C, long S, int N, int lt, const int32_
                   double* dq, double* Leq2, double* nkeff, double* Qref,
                   int32_t* sorted, int32_t* any_unsorted, void* stream);
 
+// dedicated fused-Keff binning kernel (hist_keff.cu): 0 launched, 1 not applicable, 2 error
+int hist_keff_try(const void* q, int q_dtype, long S, long P, const double* edges, int N,
+                  const void* dA, int dA_dtype, const StencilArgs* st, int C,
+                  double* part, void* stream);
+
 // levels (+ optional per-'time'-branch edges in the same launch); clears *flag_to_clear
 int minmax_levels_impl(const void* q, int q_dtype, long S, long P, int N, int increase, int out_dtype,
                        double* levels, double* minmax, double* edges, int32_t* decreasing,
