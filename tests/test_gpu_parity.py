@@ -288,6 +288,19 @@ def test_lwa_variant2_and_masks(ops, vort):
             for j, m in zip([3, 60, 100], masks):
                 got = ops.lwa_mask(dev(ops, q3), dev(ops, Q), j, increase, variant).cpu().numpy()
                 assert np.array_equal(got, m)                      # integer masks bit-exact
+            for part in ("upper", "lower"):
+                refp = O.cal_local_wave_activity(q3, Q, dA2, lat2, increase, part, variant=variant)
+                outp = ops.lwa(dev(ops, q3), dev(ops, Q), ww, increase, part, variant).cpu().numpy()
+                assert relmax(outp, refp) <= RTOL_FIELD * 1e-2
+        # variant 2 with an unsorted profile and NaN cells takes the exact kernel
+        Qs = Q.copy(); Qs[0, 5], Qs[0, 50] = Qs[0, 50], Qs[0, 5]
+        q4 = q3.copy(); q4[0, 7, 3:9] = np.nan
+        ref = O.cal_local_wave_activity(q4, Qs, dA2, lat2, increase, "all", variant=2)
+        out = ops.lwa(dev(ops, q4), dev(ops, Qs), ww, increase, "all", 2).cpu().numpy()
+        assert relmax(out, ref) <= RTOL_FIELD * 1e-2
+        ref = O.cal_local_wave_activity(q4, Q, dA2, lat2, increase, "all", variant=2)
+        out = ops.lwa(dev(ops, q4), dev(ops, Q), ww, increase, "all", 2).cpu().numpy()
+        assert relmax(out, ref) <= RTOL_FIELD * 1e-2
 
 
 def test_lape_xz_plane_with_topography(ops):

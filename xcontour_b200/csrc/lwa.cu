@@ -320,6 +320,88 @@ k_lwa_fast(const QT* __restrict__ q, long s0, int ny, int nx,
     }
 }
 
+// Variant 2 (cal_local_wave_activity2, core.py:802-905: the point is fixed, the
+// profile varies).  With a sorted profile it needs no scatter at all:
+//   out[j] = sg * ( [hi<j] (v (W_j - W_hi) - (QW_j - QW_hi))  -  [lo>j] (v (W_lo - W_j) - (QW_lo - QW_j)) )
+// with v = sg*q[j][i], lo = #{Q < v}, hi = #{Q <= v} and the column prefix sums
+// W_k = sum_{j'<k} ww[j'][i], QW_k = sum_{j'<k} Q_j' ww[j'][i].  One warp per column
+// builds the two prefix arrays in shared memory, then every row is a gather.
+constexpr int LWA2_TC = 8;
+template <typename QT>
+__global__ void __launch_bounds__(LWA2_TC * 32)
+k_lwa2_fast(const QT* __restrict__ q, long s0, int ny, int nx,
+            const double* __restrict__ Qref, const double* __restrict__ ww,
+            int increase, int part, const int32_t* __restrict__ sorted, double* __restrict__ out)
+{
+    const long s = s0 + blockIdx.y;
+    if (!sorted[s]) return;
+    extern __shared__ __align__(16) unsigned char smem[];
+    double*   Qs  = reinterpret_cast<double*>(smem);                       // [ny]
+    double2*  PW  = reinterpret_cast<double2*>(Qs + ((ny + 1) & ~1));      // [TC][ny+1] (W, QW)
+    uint32_t* lut = reinterpret_cast<uint32_t*>(PW + (size_t)LWA2_TC * (ny + 1));
+    uint16_t* first = reinterpret_cast<uint16_t*>(lut + LWA_LUT);          // [LWA_LUT+1]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
+    const double sg = increase ? 1.0 : -1.0;
+    const QT* qs = q + s * (long)ny * nx;
+    const double* Qg = Qref + s * (long)ny;
+    for (int j = tid; j < ny; j += nthr) Qs[j] = sg * Qg[j];
+    __syncthreads();
+    const double qmin = Qs[0], qmax = Qs[ny - 1];
+    const float qminf = (float)qmin;
+    const float scalef = (qmax > qmin) ? (float)((double)LWA_LUT / (qmax - qmin)) : 0.0f;
+    for (int j = tid; j <= ny; j += nthr) {
+        const int bj = (j < ny) ? lwa_bucket((float)Qs[j], qminf, scalef) : LWA_LUT;
+        const int bp = (j > 0) ? lwa_bucket((float)Qs[j - 1], qminf, scalef) : -1;
+        for (int b = bp + 1; b <= bj; ++b) first[b] = (uint16_t)j;
+    }
+    __syncthreads();
+    for (int b = tid; b < LWA_LUT; b += nthr) lut[b] = (uint32_t)first[b] | ((uint32_t)first[b + 1] << 16);
+
+    const int i = blockIdx.x * LWA2_TC + warp;                             // this warp's column
+    const bool col_ok = i < nx;
+    double2* P = PW + (size_t)warp * (ny + 1);
+    // column prefix sums, 32 rows per step (NaN weights contribute nothing: nansum)
+    double cW = 0.0, cQ = 0.0;
+    for (int r0 = 0; r0 < ny; r0 += 32) {
+        const int j = r0 + lane;
+        double w = (j < ny && col_ok) ? __ldg(ww + (long)j * nx + i) : 0.0;
+        if (w != w) w = 0.0;
+        double xw = w, xq = (j < ny) ? sg * Qs[j] * w : 0.0;                // Q_j (original sign) * ww
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double tw = __shfl_up_sync(XC_FULL, xw, o), tq = __shfl_up_sync(XC_FULL, xq, o);
+            if (lane >= o) { xw += tw; xq += tq; }
+        }
+        if (j < ny) P[j + 1] = make_double2(cW + xw, cQ + xq);
+        cW += __shfl_sync(XC_FULL, xw, 31); cQ += __shfl_sync(XC_FULL, xq, 31);
+    }
+    if (lane == 0) P[0] = make_double2(0.0, 0.0);
+    __syncthreads();                                                       // lut + prefix arrays ready
+
+    const bool keep_pos = (part == XC_PART_UPPER) == (increase != 0);
+    const bool use_t1 = (part == XC_PART_ALL) || !keep_pos;   // rows j' <  j (mask -1 region)
+    const bool use_t2 = (part == XC_PART_ALL) || keep_pos;    // rows j' >= j (mask +1 region)
+    if (!col_ok) return;
+    for (int j = lane; j < ny; j += 32) {
+        const double qv = (double)__ldg(qs + (long)j * nx + i);
+        double res = 0.0;
+        if (qv == qv) {
+            const double v = sg * qv;
+            const uint32_t pk = lut[lwa_bucket((float)v, qminf, scalef)];
+            int x = (int)(pk & 0xffffu), e = (int)(pk >> 16);
+            while (x < e) { const int mid = (x + e) >> 1; if (Qs[mid] < v) x = mid + 1; else e = mid; }
+            const int lo = x;
+            int hi = lo;
+            while (hi < ny && Qs[hi] == v) ++hi;
+            const double2 pj = P[j];
+            // sums use the original-sign profile: sum (q - Q_j') ww = qv*dW - dQW
+            if (use_t1 && hi < j) { const double2 a = P[hi]; res += qv * (pj.x - a.x) - (pj.y - a.y); }
+            if (use_t2 && lo > j) { const double2 b = P[lo]; res -= qv * (b.x - pj.x) - (b.y - pj.y); }
+        }
+        out[(s * ny + j) * (long)nx + i] = res;
+    }
+}
+
 // Exact reference loop (any profile, both variants).  Persistent grid: each CTA
 // walks (slice, tile) work items; slices already handled by k_lwa_fast are
 // skipped.  block = (32, 8): 32 columns x 8 output rows.
@@ -515,17 +597,35 @@ int xc::lwa_impl(const void* q, int q_dtype, long S, int n_eq, int n_x, const do
                        : launch_lwa_fast<double, false>((const double*)q, S, n_eq, n_x, Qref, ww, increase, part, sorted, out, tc, st);
         if (rc) return rc;
     }
-    // exact loop for whatever the fast path did not take (exits at once when the
+    const size_t sm2 = (size_t)((n_eq + 1) & ~1) * 8 + (size_t)LWA2_TC * (n_eq + 1) * 16 +
+                       (size_t)LWA_LUT * 4 + (size_t)(LWA_LUT + 2) * 2;
+    const bool fast2 = (variant == 2) && n_eq < 65535 && sm2 <= 227 * 1024;
+    if (fast2) {
+        k_check_sorted<<<(unsigned)S, 256, 0, st>>>(Qref, n_eq, increase, sorted);
+        XC_LAUNCH_OK();
+        if (q_dtype == XC_F32) XC_CUDA_OK(cudaFuncSetAttribute(k_lwa2_fast<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+        else                   XC_CUDA_OK(cudaFuncSetAttribute(k_lwa2_fast<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+        for (long s0 = 0; s0 < S; s0 += 65535) {
+            const long ns = S - s0 < 65535 ? S - s0 : 65535;
+            dim3 grid((unsigned)((n_x + LWA2_TC - 1) / LWA2_TC), (unsigned)ns);
+            if (q_dtype == XC_F32)
+                k_lwa2_fast<float><<<grid, LWA2_TC * 32, sm2, st>>>((const float*)q, s0, n_eq, n_x, Qref, ww, increase, part, sorted, out);
+            else
+                k_lwa2_fast<double><<<grid, LWA2_TC * 32, sm2, st>>>((const double*)q, s0, n_eq, n_x, Qref, ww, increase, part, sorted, out);
+            XC_LAUNCH_OK();
+        }
+    }
+    // exact loop for whatever the fast paths did not take (exits at once when the
     // fused epilogue reported that every profile is sorted)
     dim3 blk(32, 8);
     const bool gated = fast && flags_ready && any_unsorted;
     unsigned nb = (unsigned)(sm_count() * (gated ? 1 : 8));
     if (q_dtype == XC_F32)
         k_lwa_brute<float><<<nb, blk, 0, st>>>((const float*)q, S, n_eq, n_x, Qref, ww, increase, part,
-                                               variant, fast ? sorted : nullptr, gated ? any_unsorted : nullptr, out);
+                                               variant, (fast || fast2) ? sorted : nullptr, gated ? any_unsorted : nullptr, out);
     else
         k_lwa_brute<double><<<nb, blk, 0, st>>>((const double*)q, S, n_eq, n_x, Qref, ww, increase, part,
-                                                variant, fast ? sorted : nullptr, gated ? any_unsorted : nullptr, out);
+                                                variant, (fast || fast2) ? sorted : nullptr, gated ? any_unsorted : nullptr, out);
     XC_LAUNCH_OK();
     return 0;
 }
