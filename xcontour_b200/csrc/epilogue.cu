@@ -68,6 +68,8 @@ __global__ void __launch_bounds__(256) k_scan_epilogue(const EpiParams p)
     double* sg = sa + N;                            // intgrdS[N]
     double* sc = sg + N;                            // ctr    [N]
     double* sl = sc + N;                            // latEq  [N]
+    double* stab = sl + N;                          // A(Yeq) table       [n_table]
+    double* scrd = stab + p.n_table;                // table coordinates  [n_table]
     __shared__ double wtot[8];
     const long s = blockIdx.x;
     const int tid = threadIdx.x;
@@ -90,6 +92,7 @@ __global__ void __launch_bounds__(256) k_scan_epilogue(const EpiParams p)
         (k == 0 ? sa : sg)[n] = acc;
     }
     for (int n = tid; n < N; n += blockDim.x) sc[n] = p.ctr[s * N + n];
+    for (int n = tid; n < p.n_table; n += blockDim.x) { stab[n] = p.table[n]; scrd[n] = p.table_coord[n]; }
     __syncthreads();
     block_scan(sa, N, wtot);
     block_scan(sg, N, wtot);
@@ -109,9 +112,9 @@ __global__ void __launch_bounds__(256) k_scan_epilogue(const EpiParams p)
         __syncthreads();
     }
     // latEq = Table.lookup_coordinates(area): direction from the table (core.py:1122-1126)
-    const bool trev = !(p.table[p.n_table - 1] > p.table[0]);
+    const bool trev = !(stab[p.n_table - 1] > stab[0]);
     for (int n = tid; n < N; n += blockDim.x)
-        sl[n] = np_interp(sa[n], p.table, p.table_coord, p.n_table, trev);
+        sl[n] = np_interp(sa[n], stab, scrd, p.n_table, trev);
     __syncthreads();
     for (int n = tid; n < N; n += blockDim.x) {
         const size_t o = (size_t)s * N + n;
@@ -170,7 +173,7 @@ int xc::scan_epilogue(const double* part, int C, long S, int N, int lt, const in
     p.eq_coord = eq_coord; p.ny = ny; p.keff_mask = keff_mask; p.increase = increase;
     p.area = area; p.intg = intg; p.latEq = latEq; p.Lmin = Lmin; p.dint = dint; p.dq = dq;
     p.Leq2 = Leq2; p.nkeff = nkeff; p.Qref = Qref; p.sorted = sorted; p.any_unsorted = any_unsorted;
-    const size_t sm = (size_t)4 * N * sizeof(double);
+    const size_t sm = ((size_t)4 * N + 2 * (size_t)n_table) * sizeof(double);
     XC_REQUIRE(sm <= 200 * 1024, "xc_keff_lwa_batch: N too large for the fused epilogue");
     if (sm > 48 * 1024)
         XC_CUDA_OK(cudaFuncSetAttribute(k_scan_epilogue, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));

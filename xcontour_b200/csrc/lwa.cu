@@ -62,8 +62,10 @@ __global__ void k_check_sorted(const double* __restrict__ Q, int ny, int increas
 #endif
 constexpr int LWA_NI  = XC_LWA_NI;
 constexpr int LWA_BIG = 32 * LWA_NI;       // rows per staged block
-constexpr int LWA_RSW = LWA_BIG + 2;       // staging row stride of ww (doubles)
-constexpr int LWA_RSQ = LWA_BIG + 4;       // staging row stride of q
+// staging strides chosen so that the transposed store [col][row] of a 2-row x 16-col
+// warp tile and the stride-NI column reads are both free of bank conflicts
+constexpr int LWA_RSW = LWA_BIG + 1;       // ww (doubles): odd
+constexpr int LWA_RSQ = LWA_BIG + 2;       // q: == 2 (mod 32) for BIG = 96
 
 struct LwaSmem {
     size_t off_Q, off_D, off_lut, off_tag, off_sq, off_sw, total;
