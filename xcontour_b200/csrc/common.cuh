@@ -70,6 +70,21 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
+// Byte "tag" election in shared memory (used by the warp-private scatter-adds):
+// several lanes may store different ids to the same byte at once and exactly one
+// value sticks.  The accesses are RELAXED ATOMIC stores/loads at CTA scope -- they
+// compile to ordinary STS.U8 / LDS.U8, but being morally strong they do not
+// constitute a data race under the PTX memory model (this is the classic
+// SDK-histogram "tagged write" idiom, stated in terms of the formal model).
+__device__ __forceinline__ void tag_store(uint8_t* p, unsigned v) {
+    asm volatile("st.relaxed.cta.shared.u8 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned tag_load(const uint8_t* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.cta.shared.u8 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+
 // np.interp for one x against ascending xp[0..n) / fp[0..n) with numpy's exact
 // arithmetic (numpy/_core/src/multiarray/compiled_base.c, arr_interp): clamp to
 // the end values, return fp[j] on an exact hit, otherwise

@@ -123,9 +123,9 @@ __device__ __forceinline__ void scatter_add4(double* H, uint8_t* tag, const int 
             bool active = bin[u] >= 0;
             unsigned pending = __ballot_sync(XC_FULL, active);
             while (pending) {
-                if (active) tag[bin[u]] = (uint8_t)lane;
+                if (active) tag_store(tag + bin[u], (unsigned)lane);
                 __syncwarp();
-                if (active && tag[bin[u]] == (uint8_t)lane) {
+                if (active && tag_load(tag + bin[u]) == (unsigned)lane) {
                     rmw_add<K>(H + (size_t)bin[u] * K, w[u]);
                     active = false;
                 }

@@ -73,9 +73,9 @@ __device__ __forceinline__ void hk_tag(double2* H, uint8_t* tag, int bin, double
     bool a = bin >= 0;
     unsigned pending = __ballot_sync(XC_FULL, a);
     while (pending) {
-        if (a) tag[bin] = (uint8_t)lane;
+        if (a) tag_store(tag + bin, (unsigned)lane);
         __syncwarp();
-        if (a && tag[bin] == (uint8_t)lane) {
+        if (a && tag_load(tag + bin) == (unsigned)lane) {
             double2 t = H[bin]; t.x += w0; t.y += w1; H[bin] = t;
             a = false;
         }

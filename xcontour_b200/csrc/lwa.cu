@@ -55,7 +55,7 @@ __global__ void k_check_sorted(const double* __restrict__ Q, int ny, int increas
 #define XC_LWA_UPFRONT 0
 #endif
 #ifndef XC_LWA_MINB          /* min blocks per SM given to __launch_bounds__ (0 = unspecified) */
-#define XC_LWA_MINB 0
+#define XC_LWA_MINB 1
 #endif
 #ifndef XC_LWA_BISECT        /* unrolled branch-free bisection steps before the fallback loop */
 #define XC_LWA_BISECT 0
@@ -137,9 +137,9 @@ __device__ __forceinline__ void lwa_scatter(double2* Dw, uint8_t* tagw, const in
             bool a = act[u];
             unsigned pending = __ballot_sync(XC_FULL, a);
             while (pending) {
-                if (a) tagw[target[u]] = (uint8_t)lane;
+                if (a) tag_store(tagw + target[u], (unsigned)lane);
                 __syncwarp();
-                if (a && tagw[target[u]] == (uint8_t)lane) {
+                if (a && tag_load(tagw + target[u]) == (unsigned)lane) {
                     double2 t = Dw[target[u]]; t.x += nw[u]; t.y += nwv[u]; Dw[target[u]] = t;
                     a = false;
                 }
