@@ -529,3 +529,109 @@ def test_full_size_properties(ops):
     out2 = plan.run(qd, out=plan.alloc_outputs(2))
     torch.cuda.synchronize()
     assert torch.equal(out2["lwa"], out["lwa"]) and torch.equal(out2["nkeff"].nan_to_num(), out["nkeff"].nan_to_num())
+
+
+# ---------------------------------------------------------------- more shapes / options
+def test_fused_batch_fp64_tracer_grds_input_odd_sizes(ops):
+    """fp64 tracer, |grad q|^2 given as an input array (fp32 and fp64), nx not a
+    multiple of 4, descending latitude coordinate, fp64 contour dtype, part='upper'."""
+    from xcontour_b200.pipeline import KeffLwaPlan
+    rng = np.random.default_rng(17)
+    ny, nx, S, N = 73, 145, 3, 37
+    lat = np.linspace(88.0, -88.0, ny)                       # descending
+    lon = np.arange(nx) * (360.0 / nx)
+    phi, lam = np.deg2rad(lat)[:, None], np.deg2rad(lon)[None, :]
+    q = np.stack([np.sin(phi) + 0.25 * np.cos(phi) ** 2 * np.sin(5 * lam + s) +
+                  0.02 * rng.standard_normal((ny, nx)) for s in range(S)])          # fp64
+    dA = O.latlon_cell_area(lat, lon)                                              # fp64
+    for gdt in (np.float32, np.float64):
+        grd = np.abs(rng.standard_normal(q.shape)).astype(gdt) * 1e-10
+        for increase, lt, part in ((False, True, "all"), (False, False, "upper")):
+            plan = KeffLwaPlan(lat, lon, dA, N, increase=increase, lt=lt, dtype=np.float64, part=part)
+            out = plan.run(dev(ops, q), grdS=dev(ops, grd))
+            torch.cuda.synchronize()
+            ctr = O.cal_contours(q, N, increase, np.float64)
+            assert np.array_equal(out["ctr"].cpu().numpy(), ctr)
+            tbl, c = O.cal_area_eqCoord_table_hist(lat, np.ones((ny, nx)), dA, 0, increase, lt)
+            area = O.cal_integral_within_contours_hist(q, ctr, dA, lt)
+            intg = O.cal_integral_within_contours_hist(q, ctr, dA, lt, integrand=grd)
+            assert relmax(out["area"].cpu().numpy(), area) <= RTOL_INT
+            assert relmax(out["intgrdS"].cpu().numpy(), intg) <= RTOL_INT
+            latEq = O.table_lookup_coordinates(area, tbl, c)
+            _close(out["latEq"].cpu().numpy(), latEq, 1e-11)
+            Qref = O.interp_to_coords(lat, latEq, ctr)
+            _close(out["Qref"].cpu().numpy(), Qref, 1e-11)
+            refL = O.cal_local_wave_activity(q, out["Qref"].cpu().numpy(), dA, lat, increase, part)
+            assert relmax(out["lwa"].cpu().numpy(), refL) <= RTOL_FIELD * 1e-2
+
+
+def test_contour2d_plane_orientations_and_leading_dims(ops):
+    """Equivalent dimension stored last (lon, lat) and a (time, level) stack: the
+    host layer transposes for the kernels and restores the caller's dim order."""
+    import xcontour_b200 as xb
+    lat, lon, q = synth_c4(4, 46, 90)
+    dA = O.latlon_cell_area(lat, lon).astype(np.float32)
+    q4 = q.reshape(2, 2, 46, 90)
+    qT = np.ascontiguousarray(q4.transpose(0, 1, 3, 2))                # (time, level, lon, lat)
+    coords = {"time": np.arange(2), "level": np.array([300, 350]), "lat": lat, "lon": lon}
+    tr = xb.DataArray(qT, dims=("time", "level", "lon", "lat"), coords=coords, name="pv")
+    dAx = xb.DataArray(dA, dims=("lat", "lon"), coords={"lat": lat, "lon": lon})
+    mask = xb.DataArray(np.ones((46, 90), np.float32), dims=("lat", "lon"), coords={"lat": lat, "lon": lon})
+    an = xb.Contour2D(tr, dAx, dims={"X": "lon", "Y": "lat"}, dimEq={"Y": "lat"}, increase=True, lt=True)
+    ctr = an.cal_contours(31)
+    assert ctr.dims == ("time", "level", "contour")
+    ref_ctr = O.cal_contours(q, 31, True).reshape(2, 2, 31)
+    assert np.array_equal(ctr.values, ref_ctr)
+    area = an.cal_integral_within_contours_hist(ctr)
+    ref_area = O.cal_integral_within_contours_hist(q, ref_ctr.reshape(4, 31), dA, True).reshape(2, 2, 31)
+    assert relmax(area.values, ref_area) <= RTOL_INT
+    table = an.cal_area_eqCoord_table_hist(mask)
+    latEq = table.lookup_coordinates(area)
+    Q = an.interp_to_coords(xb.DataArray(lat, dims=("lat",), coords={"lat": lat}), latEq, ctr)
+    assert Q.dims == ("time", "level", "lat")
+    lwa = an.cal_local_wave_activity(tr, Q)
+    assert lwa.dims == tr.dims
+    refL = O.cal_local_wave_activity(q, Q.values.reshape(4, 46), dA, lat, True).reshape(2, 2, 46, 90)
+    assert relmax(lwa.values.transpose(0, 1, 3, 2), refL) <= RTOL_FIELD * 1e-2
+    lwa2 = an.cal_local_wave_activity2(tr, Q)
+    refL2 = O.cal_local_wave_activity(q, Q.values.reshape(4, 46), dA, lat, True, variant=2).reshape(2, 2, 46, 90)
+    assert relmax(lwa2.values.transpose(0, 1, 3, 2), refL2) <= RTOL_FIELD * 1e-2
+
+
+def test_contours_at_and_contour_means(ops, vort):
+    """cal_contours_at_hist (core.py:316-360) and the along-contour means
+    (core.py:491-616) are compositions of the kernels above."""
+    import xcontour_b200 as xb
+    lat, lon, q = vort
+    q = q[::2, ::2].copy(); lat = lat[::2].copy(); lon = lon[::2].copy()
+    dA = O.latlon_cell_area(lat, lon).astype(np.float32)
+    rng = np.random.default_rng(3)
+    g = np.abs(rng.standard_normal(q.shape)).astype(np.float32)
+    f = rng.standard_normal(q.shape).astype(np.float32)
+    coords = {"latitude": lat, "longitude": lon}
+    tr = xb.DataArray(q, dims=("latitude", "longitude"), coords=coords, name="vor")
+    gx = xb.DataArray(g, dims=("latitude", "longitude"), coords=coords, name="grd")
+    fx = xb.DataArray(f, dims=("latitude", "longitude"), coords=coords, name="f")
+    dAx = xb.DataArray(dA, dims=("latitude", "longitude"), coords=coords)
+    mask = xb.DataArray(np.ones_like(q), dims=("latitude", "longitude"), coords=coords)
+    an = xb.Contour2D(tr, dAx, dims={"X": "longitude", "Y": "latitude"}, dimEq={"Y": "latitude"},
+                      increase=True, lt=True)
+    table = an.cal_area_eqCoord_table_hist(mask)
+    pre = np.linspace(-80, 80, 33).astype(np.float32)
+    qat = an.cal_contours_at_hist(pre, table)
+    ctr = O.cal_contours(q[None], 33, True)
+    area = O.cal_integral_within_contours_hist(q[None], ctr[0], dA, True)
+    tbl, c = O.cal_area_eqCoord_table_hist(lat, np.ones_like(q), dA, 0, True, True)
+    ref = O.interp_to_coords(pre, O.table_lookup_coordinates(area, tbl, c), ctr)[0]
+    assert qat.dims == ("contour",) and qat.name == "vor"
+    _close(qat.values, ref, 1e-11)
+    c61 = an.cal_contours(61)
+    cm = an.cal_contour_mean_hist(c61, fx, gx)
+    ref61 = O.cal_contours(q[None], 61, True)
+    a61 = O.cal_integral_within_contours_hist(q[None], ref61[0], dA, True)
+    with np.errstate(all="ignore"):
+        up = O.cal_gradient_wrt_area(O.cal_integral_within_contours_hist(q[None], ref61[0], dA, True, integrand=(f * g)[None]), a61)
+        lo = O.cal_gradient_wrt_area(O.cal_integral_within_contours_hist(q[None], ref61[0], dA, True, integrand=g[None]), a61)
+        refcm = (up / lo)[0]
+    assert cm.name == "cmf"
+    _close(cm.values, refcm, 1e-8)
