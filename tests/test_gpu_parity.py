@@ -635,3 +635,37 @@ def test_contours_at_and_contour_means(ops, vort):
         refcm = (up / lo)[0]
     assert cm.name == "cmf"
     _close(cm.values, refcm, 1e-8)
+
+
+def test_error_conventions_and_degenerate_inputs(ops):
+    """Bare Exceptions with the reference's messages; degenerate slices."""
+    import xcontour_b200 as xb
+    lat = np.linspace(-60, 60, 13).astype(np.float32); lon = np.arange(24, dtype=np.float32) * 15
+    q = np.zeros((13, 24), np.float32) + 2.5                       # constant tracer
+    tr = xb.DataArray(q, dims=("lat", "lon"), coords={"lat": lat, "lon": lon}, name="c")
+    dAx = xb.DataArray(np.ones((13, 24), np.float32), dims=("lat", "lon"))
+    an = xb.Contour2D(tr, dAx, dims={"X": "lon", "Y": "lat"}, dimEq={"Y": "lat"}, increase=True, lt=True)
+    ctr = an.cal_contours(5)
+    assert np.array_equal(ctr.values, np.full(5, 2.5, np.float32))
+    with pytest.raises(Exception, match="non monotonic bins"):       # core.py:1233-1240
+        an.cal_integral_within_contours_hist(ctr)
+    with pytest.raises(Exception, match="predef should be a 1D array"):
+        an.cal_contours_at_hist(np.zeros((2, 2)), None)
+    # strict path on the constant tracer: nothing is < 2.5, everything is < 3
+    lv = np.array([2.0, 2.5, 3.0], np.float32)
+    a = an.cal_integral_within_contours(lv)
+    assert a.values.tolist() == [0.0, 0.0, 13 * 24.0]
+    # all-NaN slice: levels are NaN, like nanmin/nanmax of an empty set
+    qn = np.full((2, 4, 8), np.nan, np.float32); qn[1] = np.arange(32, dtype=np.float32).reshape(4, 8)
+    lv, mm = ops.minmax_levels(dev(ops, qn.reshape(2, -1)), 4, True, 0)
+    lv = lv.cpu().numpy()
+    assert np.isnan(lv[0]).all() and np.array_equal(lv[1].astype(np.float32), O.cal_contours(qn[1:], 4, True)[0])
+    # argument errors come back through xc_last_error
+    with pytest.raises(Exception, match="N>=2"):
+        ops.minmax_levels(dev(ops, qn.reshape(2, -1)), 1, True, 0)
+    t = xb.Table(xb.DataArray(np.array([0.0, 1.0, 3.0]), dims=("lat",), coords={"lat": np.array([-1.0, 0.0, 1.0])}), "lat")
+    assert np.allclose(t.lookup_coordinates(np.array([0.5, 2.0, 9.0])), [-0.5, 0.5, 1.0])
+    assert np.allclose(t.lookup_values(np.array([-0.5, 0.5])), [0.5, 2.0])
+    with pytest.raises(Exception, match="not every time or level"):
+        xb.Table(xb.DataArray(np.array([[0.0, 1.0], [1.0, 0.0]]), dims=("t", "lat"),
+                              coords={"lat": np.array([0.0, 1.0])}), "lat")

@@ -10,9 +10,13 @@
 // Why warp-private, non-atomic histograms: sm_100a has no native shared-memory
 // fp64 (or 64-bit integer) add -- atomicAdd(double*) on shared memory compiles
 // to an ATOMS.CAST.SPIN loop -- so each warp owns a copy and resolves the lanes
-// that hit the same bin itself: every pending lane writes its lane id into a
-// byte tag for its bin, the lane that reads its own id back owns the bin for
-// this round and does a plain 128-bit read-modify-write, the rest retry.
+// that hit the same bin itself: one MATCH.ANY gives every lane the mask of its
+// peers and the lowest remaining peer of each group does a plain 128-bit
+// read-modify-write per round (default); alternatively every pending lane
+// stores its id into a byte tag of the bin and the lane that reads its own id
+// back owns the bin for the round (XCB200_HIST_DEDUP=t).  Bins too many for
+// private copies (e.g. N = 2048 with two accumulators) fall back to shared copies
+// with CAS atomics.  The fused Keff pass has a specialised kernel in hist_keff.cu.
 #include "common.cuh"
 #include "internal.h"
 #include "grad2.cuh"

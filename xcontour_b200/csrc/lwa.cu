@@ -10,11 +10,15 @@
 //     hi(v) <= j <= j'    when hi(v) = #{Q <= v} <= j'     (mask +1 region)
 // so a column is two difference arrays (sum w, sum w*v) followed by one prefix
 // sum:  LWA[j] = V[j] - Q_j * S[j].   One warp owns one column (difference
-// arrays in shared memory, lanes walk 32 rows at a time); lo/hi come from a
-// 2048-bucket lookup table over Q plus a short exact search.  The slot j'+1 of
-// each cell is written without conflicts; the other end of the range is a
-// warp-private scatter resolved with the same byte-tag protocol as hist.cu.
-// Profiles that are not sorted (or contain NaN) take the exact O(n_eq^2) kernel.
+// arrays in shared memory; rows are staged 96 at a time through a transposed
+// tile so that global loads stay coalesced); lo/hi come from a 2048-bucket lookup
+// table over Q plus a short exact search (comparisons against Q decide, never
+// arithmetic).  The slot j'+1 of each cell is updated without conflicts; the other
+// end of the range is a warp-private scatter whose colliding lanes are serialised
+// by a byte-tag election (default) or a MATCH.ANY peel, as in hist.cu.
+// Profiles that are not sorted (or contain NaN) take the exact O(n_eq^2) kernel;
+// variant 2 (cal_local_wave_activity2) has its own gather-only kernel.
+// Bound: shared-memory scatter throughput, not HBM (profiles/README.md).
 #include "common.cuh"
 #include "internal.h"
 #include <math_constants.h>
