@@ -280,6 +280,34 @@ def interp_to_coords(predef, eqCoords, var):
     return out
 
 
+def cal_contours_equal_area(q, dA, levels, increase=True, lt=True, dtype=np.float32, refine=8):
+    """Equal-area levels by a weighted-quantile histogram (NOT in the reference --
+    north_star kernel (1); the oracle of Contour2D.cal_contours_equal_area):
+    fine equally spaced levels -> area CDF (histogram path) -> np.interp of the
+    inverse relation at `levels` equally spaced areas."""
+    N = int(levels)
+    fine = cal_contours(q, (N - 1) * int(refine) + 1, increase, dtype)
+    per = fine if q.shape[0] > 1 else fine[0]
+    area = cal_integral_within_contours_hist(q, per, dA, lt)
+    w = np.linspace(0.0, 1.0, N)
+    tgt = area[:, :1] + (area[:, -1:] - area[:, :1]) * w[None, :]
+    inc = bool(area[0, 0] < area[0, -1])
+    out = np.stack([interp1d(tgt[s], area[s], fine[s].astype(np.float64), inc) for s in range(q.shape[0])])
+    return out.astype(dtype)
+
+
+def weighted_quantile_levels(q2d, dA, fractions):
+    """Exact weighted quantiles of one slice by sorting (the 'segmented radix sort'
+    alternative of north_star kernel (1)); used to bound the histogram method."""
+    v = np.asarray(q2d, dtype=np.float64).ravel()
+    w = np.asarray(dA, dtype=np.float64).ravel()
+    ok = ~np.isnan(v)
+    order = np.argsort(v[ok], kind="stable")
+    vs, cw = v[ok][order], np.cumsum(w[ok][order])
+    idx = np.searchsorted(cw, np.asarray(fractions) * cw[-1], side="left")
+    return vs[np.minimum(idx, len(vs) - 1)]
+
+
 # --------------------------------------------------------------------------
 # d/dA, Leq2, Keff            xcontour/core.py:463-488, 619-637, 945-966
 # --------------------------------------------------------------------------

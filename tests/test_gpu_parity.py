@@ -669,3 +669,35 @@ def test_error_conventions_and_degenerate_inputs(ops):
     with pytest.raises(Exception, match="not every time or level"):
         xb.Table(xb.DataArray(np.array([[0.0, 1.0], [1.0, 0.0]]), dims=("t", "lat"),
                               coords={"lat": np.array([0.0, 1.0])}), "lat")
+
+
+@pytest.mark.parametrize("increase,lt", [(True, True), (False, False)])
+def test_equal_area_levels_weighted_quantile_histogram(ops, vort, increase, lt):
+    """north_star kernel (1): equal-area levels from a weighted-quantile histogram.
+    Parity with the oracle's restatement, and the levels sit within one fine bin of
+    the exact weighted quantiles obtained by sorting."""
+    import xcontour_b200 as xb
+    lat, lon, q = vort
+    dA = O.latlon_cell_area(lat, lon).astype(np.float32)
+    q3 = np.stack([q, 0.5 * q[::-1]])
+    tr = xb.DataArray(q3, dims=("time", "lat", "lon"), coords={"lat": lat, "lon": lon}, name="vor")
+    an = xb.Contour2D(tr, xb.DataArray(dA, dims=("lat", "lon")), dims={"X": "lon", "Y": "lat"},
+                      dimEq={"Y": "lat"}, increase=increase, lt=lt)
+    N, refine = 41, 8
+    lev = an.cal_contours_equal_area(N, refine=refine)
+    assert lev.dims == ("time", "contour") and lev.dtype == np.float32
+    ref = O.cal_contours_equal_area(q3, dA, N, increase, lt, np.float32, refine)
+    assert np.allclose(lev.values, ref, rtol=0, atol=2e-12)           # fp32 levels: identical up to 1 ulp
+    assert np.abs(lev.values.view(np.int32) - ref.view(np.int32)).max() <= 1
+    # enclosed areas of the returned levels are equally spaced to within one fine bin
+    area = an.cal_integral_within_contours_hist(lev).values
+    d = np.diff(area, axis=1)
+    fine_bin = np.abs(area[:, -1] - area[:, 0])[:, None] / ((N - 1) * refine)
+    assert np.all(np.abs(d - d.mean(axis=1, keepdims=True)) <= 4 * fine_bin)
+    # and they bracket the exact weighted quantiles (sorting) within one fine level step
+    for s in range(2):
+        step = (q3[s].max() - q3[s].min()) / ((N - 1) * refine)
+        fr = np.linspace(0, 1, N)
+        fr = fr if increase else 1 - fr          # decreasing levels enclose the complementary fraction
+        exact = O.weighted_quantile_levels(q3[s], dA, fr)
+        assert np.abs(lev.values[s][1:-1] - exact[1:-1]).max() <= 2 * step

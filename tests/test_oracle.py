@@ -255,3 +255,18 @@ def test_gather_contour_space_gloo_world2(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert res.returncode == 0, res.stdout + res.stderr
     assert res.stdout.count("OK") == 2
+
+
+def test_equal_area_levels_oracle_vs_exact_quantiles(vort):
+    """The weighted-quantile-histogram levels (north_star kernel (1), oracle side)
+    sit within a fraction of a fine bin of the exact weighted quantiles by sorting."""
+    lat, lon, q = vort
+    dA = O.latlon_cell_area(lat, lon).astype(np.float32)
+    N, refine = 41, 8
+    for increase, lt in ((True, True), (False, False), (True, False), (False, True)):
+        lev = O.cal_contours_equal_area(q[None], dA, N, increase, lt, np.float32, refine)[0]
+        step = (q.max() - q.min()) / ((N - 1) * refine)
+        fr = np.linspace(0, 1, N)
+        exact = O.weighted_quantile_levels(q, dA, fr if increase else 1 - fr)
+        assert np.abs(lev[1:-1] - exact[1:-1]).max() <= 0.5 * step
+        assert np.all(np.diff(lev) > 0) if increase else np.all(np.diff(lev) < 0)
