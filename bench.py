@@ -260,7 +260,7 @@ def run_ours(args, rank, world, local_rank):
 
     # end to end: pinned host slices -> H2D -> fused batch -> D2H of every result
     eb = min(args.e2e_batch, B)
-    streamer = HostStreamer(plan, eb, copy_lwa=True)
+    streamer = HostStreamer(plan, eb, copy_lwa=True, nbuf=args.e2e_nbuf)
     q_host = torch.empty((B, NY, NX), dtype=torch.float32).pin_memory()
     q_host.copy_(q)
     sink = {"n": 0, "chk": 0.0}
@@ -310,7 +310,9 @@ def run_ours(args, rank, world, local_rank):
                              % (B * P * 4 / 1e6, B * P * 8 / 1e6),
                        "parallelism": "slices sharded over %d GPU(s), no data-path collective" % world},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac": ach / peak, "traffic": traffic,
+                         "traffic_note": "ncu dram bytes per launch of 16 slices (profiles/traffic.json)",
+                         "peak_source": peak_src,
                          "stage_ms_per_step": stages,
                          "pipeline": {"alg_bytes_per_slice": ALG_BYTES_PER_SLICE,
                                       "achieved": ALG_BYTES_PER_SLICE * value / world / 1e9,
@@ -320,7 +322,7 @@ def run_ours(args, rank, world, local_rank):
                     "h2d_bytes_per_step": streamer.h2d_bytes // e2e_steps,
                     "d2h_bytes_per_step": streamer.d2h_bytes // e2e_steps,
                     "timing": "CUDA events spanning pinned H2D + kernels + D2H on both streams, max over ranks",
-                    "batch": eb},
+                    "batch": eb, "buffers_in_flight": args.e2e_nbuf},
             "gpu_launches": int(launches) * world,
         }
         if world == 1 and not args.no_cpu:
@@ -341,7 +343,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="slices per step per GPU")
     ap.add_argument("--sub-batch", type=int, default=0, help="slices per internal pass (0 = auto)")
-    ap.add_argument("--e2e-batch", type=int, default=16)
+    ap.add_argument("--e2e-batch", type=int, default=8)
+    ap.add_argument("--e2e-nbuf", type=int, default=2, help="batches in flight in the end-to-end leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -121,16 +121,17 @@ class KeffLwaPlan(object):
 
 class HostStreamer(object):
     """End-to-end driver for HOST-resident tracers: pinned host slices ->
-    (H2D, fused batch, D2H of every result) with two buffers in flight so the
-    copies of batch i+1 / i-1 overlap the kernels of batch i."""
+    (H2D, fused batch, D2H of every result) with ``nbuf`` buffers in flight so the
+    copies of neighbouring batches overlap the kernels of the current one (H2D,
+    kernels and D2H of a batch are ordered on that batch's own stream)."""
 
-    def __init__(self, plan, batch, q_dtype=torch.float32, copy_lwa=True):
-        self.plan, self.batch, self.copy_lwa = plan, int(batch), copy_lwa
+    def __init__(self, plan, batch, q_dtype=torch.float32, copy_lwa=True, nbuf=3):
+        self.plan, self.batch, self.copy_lwa, self.nbuf = plan, int(batch), copy_lwa, int(nbuf)
         dev = plan.dA.device
-        self.streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
-        self.qdev = [torch.empty((batch, plan.ny, plan.nx), dtype=q_dtype, device=dev) for _ in range(2)]
-        self.outs = [plan.alloc_outputs(batch) for _ in range(2)]
-        self.ws = [torch.empty(plan.workspace_bytes(batch), dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(self.nbuf)]
+        self.qdev = [torch.empty((batch, plan.ny, plan.nx), dtype=q_dtype, device=dev) for _ in range(self.nbuf)]
+        self.outs = [plan.alloc_outputs(batch) for _ in range(self.nbuf)]
+        self.ws = [torch.empty(plan.workspace_bytes(batch), dtype=torch.uint8, device=dev) for _ in range(self.nbuf)]
         self.host = [{k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in o.items()
                       if copy_lwa or k != "lwa"} for o in self.outs]
         self.h2d_bytes = 0
@@ -140,10 +141,10 @@ class HostStreamer(object):
         """q_host: pinned CPU tensor [S, ny, nx].  ``consume(s0, s1, host_dict)`` is
         called for every finished batch (host buffers are reused afterwards)."""
         S = q_host.shape[0]
-        pending = [None, None]
+        pending = [None] * self.nbuf
         nb = (S + self.batch - 1) // self.batch
-        for b in range(nb + 2):
-            i = b % 2
+        for b in range(nb + self.nbuf):
+            i = b % self.nbuf
             if pending[i] is not None:                    # drain the batch that used buffer i
                 s0, s1, ev = pending[i]
                 ev.synchronize()
