@@ -26,13 +26,38 @@ long auto_sub_batch(long S, long P)
     const char* env = getenv("XCB200_SUB_BATCH");
     long sub = env ? atol(env) : 0;
     if (sub <= 0) {
-        // Measured on B200 (721x1440): throughput rises up to ~16 slices per pass
-        // (launch / tail overheads amortise; the kernels are issue-bound, not
-        // HBM-bound, so spilling the 126 MB L2 costs less than short launches).
-        sub = (long)(200.0e6 / (double)(P * 12));
+        // Measured on B200 (721x1440, two passes in flight): throughput rises up to
+        // ~32 slices per pass (launch / tail overheads amortise; the kernels are
+        // bound by shared-memory scatter, not by HBM, so spilling the 126 MB L2
+        // costs less than short launches).
+        sub = (long)(400.0e6 / (double)(P * 12));
         if (sub < 1) sub = 1;
     }
     return sub < S ? sub : S;
+}
+
+// internal streams/events of the two-passes-in-flight schedule, one set per host thread
+struct Overlap { cudaStream_t s[2]; cudaEvent_t fork, join[2]; int dev; };
+bool overlap_enabled()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("XCB200_OVERLAP"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+Overlap* overlap_streams()
+{
+    static thread_local Overlap ov; static thread_local bool ready = false;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    if (ready && ov.dev == dev) return &ov;
+    if (ready) return nullptr;                    // one device per host thread (one process per GPU)
+    for (int l = 0; l < 2; ++l) {
+        if (cudaStreamCreateWithFlags(&ov.s[l], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&ov.join[l], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    if (cudaEventCreateWithFlags(&ov.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    ov.dev = dev; ready = true;
+    return &ov;
 }
 
 FusedPlan fused_plan(long S, int ny, int nx, int N, long sub_req)
@@ -46,11 +71,12 @@ FusedPlan fused_plan(long S, int ny, int nx, int N, long sub_req)
     size_t t = 0;
     t += align_up(p.ws_minmax, 256) + align_up(p.ws_hist, 256) + align_up(p.ws_lwa, 256);
     t += align_up((size_t)p.sub * (N + 1) * 8, 256);        // edges
-    t += align_up((size_t)p.sub * 4, 256);                  // decreasing
+    t += 2 * align_up((size_t)p.sub * 4, 256) + 1024;       // decreasing, sorted, flag
     t += 9 * align_up((size_t)p.sub * N * 8, 256);          // contour-space temporaries
     t += align_up((size_t)p.sub * ny * 8, 256);             // Qref
+    t *= 2;                                                 // two passes in flight (one per internal stream)
     t += 2 * align_up((size_t)ny * 8, 256);                 // row metrics
-    p.total = t + 4096;
+    p.total = t + 8192;
     return p;
 }
 }  // namespace
@@ -80,31 +106,45 @@ extern "C" int xc_keff_lwa_batch(const xc_keff_lwa_args* a, void* workspace, siz
     XC_REQUIRE(workspace && ws_bytes >= pl.total, "xc_keff_lwa_batch: workspace too small (%zu < %zu)",
                ws_bytes, pl.total);
     Arena ar(workspace, ws_bytes);
-    char* w_minmax = ar.take<char>(pl.ws_minmax);
-    char* w_hist = ar.take<char>(pl.ws_hist);
-    int32_t* sorted = ar.take<int32_t>((size_t)pl.sub);
-    int32_t* any_unsorted = ar.take<int32_t>(1);
-    double* edges = ar.take<double>((size_t)pl.sub * (N + 1));
-    int32_t* decr = ar.take<int32_t>((size_t)pl.sub);
-    double* t_ctr = ar.take<double>((size_t)pl.sub * N);     double* t_area = ar.take<double>((size_t)pl.sub * N);
-    double* t_intg = ar.take<double>((size_t)pl.sub * N);    double* t_latEq = ar.take<double>((size_t)pl.sub * N);
-    double* t_Lmin = ar.take<double>((size_t)pl.sub * N);    double* t_dint = ar.take<double>((size_t)pl.sub * N);
-    double* t_dq = ar.take<double>((size_t)pl.sub * N);      double* t_Leq2 = ar.take<double>((size_t)pl.sub * N);
-    double* t_nk = ar.take<double>((size_t)pl.sub * N);
-    double* t_Q = ar.take<double>((size_t)pl.sub * ny);
+    struct Lane {
+        char *w_minmax, *w_hist; int32_t *sorted, *any_unsorted, *decr; double* edges;
+        double *t_ctr, *t_area, *t_intg, *t_latEq, *t_Lmin, *t_dint, *t_dq, *t_Leq2, *t_nk, *t_Q;
+    } lanes[2];
+    for (Lane& L : lanes) {
+        L.w_minmax = ar.take<char>(pl.ws_minmax);
+        L.w_hist = ar.take<char>(pl.ws_hist);
+        L.sorted = ar.take<int32_t>((size_t)pl.sub);
+        L.any_unsorted = ar.take<int32_t>(1);
+        L.edges = ar.take<double>((size_t)pl.sub * (N + 1));
+        L.decr = ar.take<int32_t>((size_t)pl.sub);
+        L.t_ctr = ar.take<double>((size_t)pl.sub * N);   L.t_area = ar.take<double>((size_t)pl.sub * N);
+        L.t_intg = ar.take<double>((size_t)pl.sub * N);  L.t_latEq = ar.take<double>((size_t)pl.sub * N);
+        L.t_Lmin = ar.take<double>((size_t)pl.sub * N);  L.t_dint = ar.take<double>((size_t)pl.sub * N);
+        L.t_dq = ar.take<double>((size_t)pl.sub * N);    L.t_Leq2 = ar.take<double>((size_t)pl.sub * N);
+        L.t_nk = ar.take<double>((size_t)pl.sub * N);    L.t_Q = ar.take<double>((size_t)pl.sub * ny);
+    }
     double* rcos = ar.take<double>((size_t)ny);
     double* dphi = ar.take<double>((size_t)ny);
     XC_REQUIRE(ar.ok(), "xc_keff_lwa_batch: workspace accounting error");
 
     StencilArgs sa; sa.ny = ny; sa.nx = nx; sa.cx = rcos; sa.cy = dphi;
     if (stencil) { if (row_metrics(a->lat_rad, ny, a->dlambda, rcos, dphi, stream)) return 1; }
-    // optional per-stage timing
     cudaStream_t st = (cudaStream_t)stream;
     const long npass = (S + pl.sub - 1) / pl.sub;
+    // optional per-stage timing (forces the serial schedule so that stages do not overlap)
     std::vector<cudaEvent_t> ev;
     if (a->stage_ms) {
         ev.resize((size_t)npass * (XC_N_STAGES + 1));
         for (auto& e : ev) XC_CUDA_OK(cudaEventCreate(&e));
+    }
+    // Two passes in flight: pass p runs start to finish on internal stream p % 2 with
+    // its own temporaries, so the HBM-bound min/max pass and the latency-bound epilogue
+    // of pass p+1 fill the gaps of the shared-memory-bound LWA kernel of pass p.
+    Overlap* ov = nullptr;
+    if (!a->stage_ms && npass >= 2 && overlap_enabled()) ov = overlap_streams();
+    if (ov) {
+        XC_CUDA_OK(cudaEventRecord(ov->fork, st));
+        for (int l = 0; l < 2; ++l) XC_CUDA_OK(cudaStreamWaitEvent(ov->s[l], ov->fork, 0));
     }
     long pass = 0;
     auto mark = [&](int k) { if (a->stage_ms) cudaEventRecord(ev[(size_t)pass * (XC_N_STAGES + 1) + k], st); };
@@ -113,19 +153,21 @@ extern "C" int xc_keff_lwa_batch(const xc_keff_lwa_args* a, void* workspace, siz
 
     for (long s0 = 0; s0 < S; s0 += pl.sub) {
         const long ns = S - s0 < pl.sub ? S - s0 : pl.sub;
+        Lane& L = lanes[pass & 1];
+        void* ps = ov ? (void*)ov->s[pass & 1] : stream;              // this pass's stream
         auto at = [&](double* user, double* tmp) { return user ? user + s0 * (long)N : tmp; };
         const void* q = (const char*)a->q + (size_t)s0 * P * qsz;
-        double* ctr = at(a->ctr, t_ctr);       double* area = at(a->area, t_area);
-        double* intg = at(a->intgrdS, t_intg); double* latEq = at(a->latEq, t_latEq);
-        double* Lmin = at(a->Lmin, t_Lmin);    double* dint = at(a->dintSdA, t_dint);
-        double* dq = at(a->dqdA, t_dq);        double* Leq2 = at(a->Leq2, t_Leq2);
-        double* nk = at(a->nkeff, t_nk);
-        double* Qref = a->Qref ? a->Qref + s0 * (long)ny : t_Q;
+        double* ctr = at(a->ctr, L.t_ctr);       double* area = at(a->area, L.t_area);
+        double* intg = at(a->intgrdS, L.t_intg); double* latEq = at(a->latEq, L.t_latEq);
+        double* Lmin = at(a->Lmin, L.t_Lmin);    double* dint = at(a->dintSdA, L.t_dint);
+        double* dq = at(a->dqdA, L.t_dq);        double* Leq2 = at(a->Leq2, L.t_Leq2);
+        double* nk = at(a->nkeff, L.t_nk);
+        double* Qref = a->Qref ? a->Qref + s0 * (long)ny : L.t_Q;
 
         mark(0);
         // (1)+(1b) min/max, levels and per-'time'-branch edges in two launches
         if (minmax_levels_impl(q, a->q_dtype, ns, P, N, a->increase, a->ctr_dtype, ctr, nullptr,
-                               edges, decr, any_unsorted, w_minmax, pl.ws_minmax, stream)) return 1;
+                               L.edges, L.decr, L.any_unsorted, L.w_minmax, pl.ws_minmax, ps)) return 1;
         mark(1);
         mark(2);
         // (2) area and int |grad q|^2 dA in one pass over q (per-CTA partials only)
@@ -133,23 +175,29 @@ extern "C" int xc_keff_lwa_batch(const xc_keff_lwa_args* a, void* workspace, siz
         const void* integs[1] = { stencil ? nullptr : (const void*)((const char*)a->grdS + (size_t)s0 * P * gsz) };
         const int integ_dt[1] = { a->grdS_dtype };
         HistOnly ho;
-        if (bin_accumulate_impl(q, a->q_dtype, ns, P, edges, N + 1, N, 0, a->dA, a->dA_dtype, 1,
+        if (bin_accumulate_impl(q, a->q_dtype, ns, P, L.edges, N + 1, N, 0, a->dA, a->dA_dtype, 1,
                                 integs, integ_dt, stencil ? 0 : 1, nullptr,
-                                a->lt ? XC_SCAN_PREFIX : XC_SCAN_TOTAL_MINUS, decr,
-                                nullptr, so, nullptr, w_hist, pl.ws_hist, stream,
+                                a->lt ? XC_SCAN_PREFIX : XC_SCAN_TOTAL_MINUS, L.decr,
+                                nullptr, so, nullptr, L.w_hist, pl.ws_hist, ps,
                                 stencil ? &sa : nullptr, &ho)) return 1;
         mark(3);
         // scan + (3) latEq + (5)/(4) Lmin, d/dA, Leq2, nkeff + (3) Q(eq_coord), one launch
-        if (scan_epilogue(ho.part, ho.C, ns, N, a->lt, decr, ctr, a->ctr_dtype == XC_F32,
+        if (scan_epilogue(ho.part, ho.C, ns, N, a->lt, L.decr, ctr, a->ctr_dtype == XC_F32,
                           a->table, a->table_coord, a->n_table, a->eq_coord, ny, a->keff_mask, a->increase,
-                          area, intg, latEq, Lmin, dint, dq, Leq2, nk, Qref, sorted, any_unsorted, stream)) return 1;
+                          area, intg, latEq, Lmin, dint, dq, Leq2, nk, Qref, L.sorted, L.any_unsorted, ps)) return 1;
         mark(4);
         // (6) LWA
         if (a->lwa)
             if (lwa_impl(q, a->q_dtype, ns, ny, nx, Qref, a->ww, a->increase, a->part, 1,
-                         a->lwa + (size_t)s0 * P, sorted, any_unsorted, true, stream)) return 1;
+                         a->lwa + (size_t)s0 * P, L.sorted, L.any_unsorted, true, ps)) return 1;
         mark(5);
         ++pass;
+    }
+    if (ov) {
+        for (int l = 0; l < 2; ++l) {
+            XC_CUDA_OK(cudaEventRecord(ov->join[l], ov->s[l]));
+            XC_CUDA_OK(cudaStreamWaitEvent(st, ov->join[l], 0));
+        }
     }
     if (a->stage_ms) {
         XC_CUDA_OK(cudaStreamSynchronize(st));
