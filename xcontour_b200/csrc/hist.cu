@@ -406,8 +406,10 @@ static HistPlan plan_hist(long S, long P, int N, int K)
     }
     pl.smem = e_bytes + (size_t)(pl.ncopy > 0 ? pl.ncopy : 0) * copy_bytes +
               (pl.priv ? (size_t)pl.warps * tag_bytes : 0);
+    // CTAs per slice: fill two resident CTAs per SM for two waves without a ragged
+    // third wave (floor, not ceil)
     long want = (long)sm_count() * 4;
-    long C = (want + S - 1) / S;
+    long C = want / S;
     long maxC = (P + 16383) / 16384;
     if (C > maxC) C = maxC;
     if (C < 1) C = 1;
