@@ -188,7 +188,7 @@ def run_ours(args, rank, world, local_rank):
     from xcontour_b200 import ops
     from xcontour_b200._lib import N_STAGES, STAGE_NAMES
     from xcontour_b200.pipeline import HostStreamer, KeffLwaPlan
-    from oracle import xcontour_oracle as O       # dA construction + cpu_baseline only
+    from xcontour_b200.utils import latlon_cell_area
 
     torch.cuda.set_device(local_rank)
     ops.require_cuda()
@@ -196,7 +196,7 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     lat, lon = grid()
-    dA = O.latlon_cell_area(lat, lon).astype(np.float32)
+    dA = latlon_cell_area(lat, lon).astype(np.float32)
     plan = KeffLwaPlan(lat, lon, dA, NLEV, increase=True, lt=True, sub_batch=args.sub_batch)
     B = args.batch
 

@@ -270,3 +270,11 @@ def test_equal_area_levels_oracle_vs_exact_quantiles(vort):
         exact = O.weighted_quantile_levels(q, dA, fr if increase else 1 - fr)
         assert np.abs(lev[1:-1] - exact[1:-1]).max() <= 0.5 * step
         assert np.all(np.diff(lev) > 0) if increase else np.all(np.diff(lev) < 0)
+
+
+def test_product_cell_area_helper_matches_oracle():
+    from xcontour_b200.utils import latlon_cell_area
+    lat = np.linspace(-90, 90, 73); lon = np.arange(144) * 2.5
+    assert np.array_equal(latlon_cell_area(lat, lon), O.latlon_cell_area(lat, lon))
+    assert np.array_equal(latlon_cell_area(lat[::-1], lon), O.latlon_cell_area(lat[::-1], lon))
+    assert abs(latlon_cell_area(lat, lon).sum() / (4 * np.pi * O.Rearth ** 2) - 1) < 1e-12

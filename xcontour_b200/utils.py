@@ -32,3 +32,24 @@ def latitude_lengths_at(lats, Rearth=Rearth):
     if Rearth != globals()['Rearth']:
         raise Exception('only the default Earth radius is supported')
     return _apply(ops.lmin, lats)
+
+
+def latlon_cell_area(lat_deg, lon_deg, Rearth=Rearth):
+    """Cell areas dA[j, i] = R^2 (sin(phi_{j+1/2}) - sin(phi_{j-1/2})) dlambda of a
+    regular lat-lon grid (cell edges midway between grid latitudes, clipped at the
+    poles).  Host-side setup helper -- the reference builds the same metric with
+    xgcm in add_latlon_metrics (utils.py:43-259, rA), which is out of scope here;
+    Contour2D itself takes dA as an argument."""
+    lat = np.asarray(lat_deg, dtype=np.float64)
+    lon = np.asarray(lon_deg, dtype=np.float64)
+    asc = lat[-1] > lat[0]
+    la = lat if asc else lat[::-1]
+    edges = np.empty(len(la) + 1)
+    edges[1:-1] = 0.5 * (la[1:] + la[:-1])
+    edges[0] = max(-90.0, la[0] - 0.5 * (la[1] - la[0]))
+    edges[-1] = min(90.0, la[-1] + 0.5 * (la[-1] - la[-2]))
+    band = Rearth ** 2 * np.diff(np.sin(np.deg2rad(edges)))
+    if not asc:
+        band = band[::-1]
+    dlam = np.deg2rad(abs(lon[1] - lon[0]))
+    return np.repeat((band * dlam)[:, None], len(lon), axis=1)
