@@ -188,6 +188,17 @@ int xc_grad2_latlon(const void* q, int q_dtype, long S, int n_y, int n_x,
                     void* out, int out_dtype, void* stream);
 
 /* ------------------------------------------------------------------------
+ * (7b) cell areas of a regular lat-lon grid, built on the device:
+ *   dA[j][i] = R^2 (sin(phi_{j+1/2}) - sin(phi_{j-1/2})) * dlambda
+ * with cell edges midway between grid latitudes, clipped at the poles (either
+ * direction of the latitude coordinate).  Replaces the rA metric the reference
+ * obtains from xgcm in add_latlon_metrics (utils.py:43-259) for this grid type.
+ * lat_deg[n_y] fp64 (degrees), dlambda_deg > 0; out[n_y][n_x] in out_dtype.
+ * ---------------------------------------------------------------------- */
+int xc_latlon_cell_area(const double* lat_deg, int n_y, int n_x, double dlambda_deg,
+                        void* out, int out_dtype, void* stream);
+
+/* ------------------------------------------------------------------------
  * (8) fused batch: Keff + LWA for B slices in one call (the path bench.py
  * times).  Chains (1) (1b) (2) (3) (4) (5) (3) (6) on device without host
  * round-trips: levels -> edges -> {area, int|grad q|^2 dA} CDFs -> latEq by

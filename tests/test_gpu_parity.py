@@ -701,3 +701,15 @@ def test_equal_area_levels_weighted_quantile_histogram(ops, vort, increase, lt):
         fr = fr if increase else 1 - fr          # decreasing levels enclose the complementary fraction
         exact = O.weighted_quantile_levels(q3[s], dA, fr)
         assert np.abs(lev.values[s][1:-1] - exact[1:-1]).max() <= 2 * step
+
+
+def test_device_cell_area(ops):
+    """f4: lat-lon cell areas built on the device equal the host helper."""
+    from xcontour_b200.utils import latlon_cell_area
+    for lat in (np.linspace(-90, 90, 73), np.linspace(88, -88, 45), np.array([-60.0, -20.0, 10.0, 35.0, 80.0])):
+        nx, dlon = 48, 7.5
+        ref = latlon_cell_area(lat, np.arange(nx) * dlon)
+        out = ops.latlon_cell_area(dev(ops, lat.astype(np.float64)), nx, dlon).cpu().numpy()
+        assert np.allclose(out, ref, rtol=1e-13, atol=0)
+        out32 = ops.latlon_cell_area(dev(ops, lat.astype(np.float64)), nx, dlon, torch.float32).cpu().numpy()
+        assert np.allclose(out32, ref.astype(np.float32), rtol=2e-7, atol=0)

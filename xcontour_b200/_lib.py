@@ -77,6 +77,7 @@ SIGNATURES = {
                             c_void_p, c_void_p]),
     "xc_grad2_latlon": (c_int, [c_void_p, c_int, c_long, c_int, c_int, c_void_p, c_double,
                                 c_void_p, c_int, c_void_p]),
+    "xc_latlon_cell_area": (c_int, [c_void_p, c_int, c_int, c_double, c_void_p, c_int, c_void_p]),
     "xc_keff_lwa_batch_workspace_bytes": (c_size_t, [c_long, c_int, c_int, c_int]),
     "xc_keff_lwa_batch": (c_int, [POINTER(KeffLwaArgs), c_void_p, c_size_t, c_void_p]),
     "xc_launch_count": (c_long, []),

@@ -34,9 +34,42 @@ k_grad2(const QT* __restrict__ q, int ny, int nx, const double* __restrict__ lat
     }
 }
 
+template <typename OT>
+__global__ void k_latlon_cell_area(const double* __restrict__ lat_deg, int ny, int nx, double dlam_deg,
+                                   OT* __restrict__ out)
+{
+    const int j = blockIdx.y;
+    __shared__ double band;
+    if (threadIdx.x == 0) {
+        const bool asc = lat_deg[ny - 1] > lat_deg[0];
+        // work on the ascending view la[k]; row j is element k of it
+        const int k = asc ? j : ny - 1 - j;
+        auto la = [&](int m) { return asc ? lat_deg[m] : lat_deg[ny - 1 - m]; };
+        double lo = (k == 0) ? fmax(-90.0, la(0) - 0.5 * (la(1) - la(0))) : 0.5 * (la(k) + la(k - 1));
+        double hi = (k == ny - 1) ? fmin(90.0, la(ny - 1) + 0.5 * (la(ny - 1) - la(ny - 2))) : 0.5 * (la(k + 1) + la(k));
+        const double d2r = 3.141592653589793 / 180.0;
+        band = kRearthG * kRearthG * (sin(hi * d2r) - sin(lo * d2r)) * (dlam_deg * d2r);
+    }
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += gridDim.x * blockDim.x)
+        out[(long)j * nx + i] = (OT)band;
+}
+
 }  // namespace xc
 
 using namespace xc;
+
+extern "C" int xc_latlon_cell_area(const double* lat_deg, int n_y, int n_x, double dlambda_deg,
+                                   void* out, int out_dtype, void* stream)
+{
+    XC_REQUIRE(lat_deg && out, "xc_latlon_cell_area: null pointer");
+    XC_REQUIRE(n_y >= 2 && n_x >= 1 && n_y <= 65535 && dlambda_deg > 0.0, "xc_latlon_cell_area: bad sizes");
+    dim3 grid((unsigned)((n_x + 255) / 256), (unsigned)n_y);
+    if (out_dtype == XC_F32) k_latlon_cell_area<float><<<grid, 256, 0, (cudaStream_t)stream>>>(lat_deg, n_y, n_x, dlambda_deg, (float*)out);
+    else                     k_latlon_cell_area<double><<<grid, 256, 0, (cudaStream_t)stream>>>(lat_deg, n_y, n_x, dlambda_deg, (double*)out);
+    XC_LAUNCH_OK();
+    return 0;
+}
 
 int xc::row_metrics(const double* lat_rad, int ny, double dlambda, double* cx, double* cy, void* stream)
 {

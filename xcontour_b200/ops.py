@@ -229,6 +229,15 @@ def grad2_latlon(q, lat_rad, dlambda, out_dtype=torch.float64):
     return out
 
 
+def latlon_cell_area(lat_deg, n_x, dlambda_deg, out_dtype=torch.float64):
+    """lat_deg[n_y] (fp64, on the GPU) -> dA[n_y, n_x] built on the device."""
+    lib = require_cuda()
+    ny = lat_deg.numel()
+    out = torch.empty((ny, n_x), dtype=out_dtype, device=lat_deg.device)
+    check(lib.xc_latlon_cell_area(_p(lat_deg), ny, int(n_x), float(dlambda_deg), _p(out), fdtype(out), stream_ptr()))
+    return out
+
+
 def launch_count():
     return _lib.load().xc_launch_count()
 
