@@ -713,3 +713,37 @@ def test_device_cell_area(ops):
         assert np.allclose(out, ref, rtol=1e-13, atol=0)
         out32 = ops.latlon_cell_area(dev(ops, lat.astype(np.float64)), nx, dlon, torch.float32).cpu().numpy()
         assert np.allclose(out32, ref.astype(np.float32), rtol=2e-7, atol=0)
+
+
+def test_contour2d_1d_area_explicit_levels_check_mono(ops, vort):
+    """dA given on the latitude axis only, explicit level arrays (core.py:251-264),
+    decreasing explicit levels, and the check_mono flag (core.py:1328-1355)."""
+    import xcontour_b200 as xb
+    lat, lon, q = vort
+    q = q[::4, ::4].copy(); lat = lat[::4].copy(); lon = lon[::4].copy()
+    dA2 = O.latlon_cell_area(lat, lon)
+    coords = {"lat": lat, "lon": lon}
+    tr = xb.DataArray(q, dims=("lat", "lon"), coords=coords, name="vor")
+    dA1 = xb.DataArray(dA2[:, 0].copy(), dims=("lat",), coords={"lat": lat})      # broadcast along lon
+    an = xb.Contour2D(tr, dA1, dims={"X": "lon", "Y": "lat"}, dimEq={"Y": "lat"}, increase=True, lt=True)
+    levs = np.linspace(q.min(), q.max(), 17).astype(np.float32)
+    ctr = an.cal_contours(levs)
+    assert ctr.dims == ("contour",) and np.array_equal(ctr.values, levs)
+    assert np.array_equal(ctr["contour"].values, levs)
+    a = an.cal_integral_within_contours_hist(ctr)
+    ref = O.cal_integral_within_contours_hist(q[None], levs, dA2, True, time_branch=False)[0]
+    assert relmax(a.values, ref) <= RTOL_INT
+    # decreasing explicit levels: same numbers in reversed order (core.py:454-455)
+    a_dec = an.cal_integral_within_contours_hist(levs[::-1].copy())
+    ref_dec = O.cal_integral_within_contours_hist(q[None], levs[::-1].copy(), dA2, True, time_branch=False)[0]
+    assert relmax(a_dec.values, ref_dec) <= RTOL_INT
+    # non-uniform explicit levels exercise the binary-search path of the binning kernel
+    nl = np.sort(np.concatenate([levs[:3], levs[3] + (levs[-1] - levs[3]) * np.linspace(0, 1, 9) ** 3])).astype(np.float32)
+    nl = np.unique(nl)
+    a_nu = an.cal_integral_within_contours(nl)
+    assert relmax(a_nu.values, O.cal_integral_within_contours(q[None], nl, dA2, True)[0]) <= RTOL_INT
+    # check_mono: many levels on a small field leave empty bins -> zero differences
+    an2 = xb.Contour2D(tr, dA1, dims={"X": "lon", "Y": "lat"}, dimEq={"Y": "lat"}, increase=True, lt=True,
+                       check_mono=True)
+    with pytest.raises(Exception, match="not monotonic var"):
+        an2.cal_integral_within_contours_hist(an2.cal_contours(4001))
