@@ -265,6 +265,7 @@ k_lwa_fast(const QT* __restrict__ q, long s0, int ny, int nx,
             {
                 const uint32_t pk = lut[lwa_bucket((float)v, qminf, scalef)];
                 int x = (int)(pk & 0xffffu), e = (int)(pk >> 16);
+                const int e0 = e;                            // end of v's bucket: rows >= e0 have Q > v
 #pragma unroll
                 for (int it = 0; it < XC_LWA_BISECT; ++it) { // branch-free bisection: 3 steps cover e - x <= 7
                     const int mid = (x + e) >> 1;
@@ -280,8 +281,8 @@ k_lwa_fast(const QT* __restrict__ q, long s0, int ny, int nx,
                 const int lo = x;                            // #{Q < v}
                 if (lo > jp + 1) { target = lo; a = a && use_t1; }
                 else {
-                    int hi = lo;                             // #{Q <= v}
-                    while (hi < ny && Qs[hi] == v) ++hi;
+                    int hi = lo;                             // #{Q <= v}; ties live in v's bucket only
+                    while (hi < e0 && Qs[hi] == v) ++hi;
                     target = hi;
                     a = a && (hi <= jp) && use_t2;
                 }
@@ -395,10 +396,11 @@ k_lwa2_fast(const QT* __restrict__ q, long s0, int ny, int nx,
             const double v = sg * qv;
             const uint32_t pk = lut[lwa_bucket((float)v, qminf, scalef)];
             int x = (int)(pk & 0xffffu), e = (int)(pk >> 16);
+            const int e0 = e;
             while (x < e) { const int mid = (x + e) >> 1; if (Qs[mid] < v) x = mid + 1; else e = mid; }
             const int lo = x;
             int hi = lo;
-            while (hi < ny && Qs[hi] == v) ++hi;
+            while (hi < e0 && Qs[hi] == v) ++hi;
             const double2 pj = P[j];
             // sums use the original-sign profile: sum (q - Q_j') ww = qv*dW - dQW
             if (use_t1 && hi < j) { const double2 a = P[hi]; res += qv * (pj.x - a.x) - (pj.y - a.y); }
