@@ -528,7 +528,12 @@ def test_full_size_properties(ops):
     # determinism
     out2 = plan.run(qd, out=plan.alloc_outputs(2))
     torch.cuda.synchronize()
-    assert torch.equal(out2["lwa"], out["lwa"]) and torch.equal(out2["nkeff"].nan_to_num(), out["nkeff"].nan_to_num())
+    # contour space is bit-reproducible (fixed reduction order, MATCH.ANY peel serves
+    # the lowest lane first); the LWA tag election may in principle pick another
+    # winner order, so the field is held to rounding level rather than bit equality
+    assert torch.equal(out2["nkeff"].nan_to_num(), out["nkeff"].nan_to_num())
+    assert torch.equal(out2["area"], out["area"]) and torch.equal(out2["Qref"], out["Qref"])
+    assert float((out2["lwa"] - out["lwa"]).abs().max()) <= 1e-13 * float(out["lwa"].abs().max())
 
 
 # ---------------------------------------------------------------- more shapes / options
