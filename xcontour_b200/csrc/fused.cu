@@ -37,7 +37,10 @@ long auto_sub_batch(long S, long P)
 }
 
 // internal streams/events of the two-passes-in-flight schedule, one set per host thread
-struct Overlap { cudaStream_t s[2]; cudaEvent_t fork, join[2]; int dev; };
+#ifndef XC_LANES
+#define XC_LANES 2       /* passes in flight */
+#endif
+struct Overlap { cudaStream_t s[XC_LANES]; cudaEvent_t fork, join[XC_LANES]; int dev; };
 bool overlap_enabled()
 {
     static int v = -1;
@@ -51,7 +54,7 @@ Overlap* overlap_streams()
     if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
     if (ready && ov.dev == dev) return &ov;
     if (ready) return nullptr;                    // one device per host thread (one process per GPU)
-    for (int l = 0; l < 2; ++l) {
+    for (int l = 0; l < XC_LANES; ++l) {
         if (cudaStreamCreateWithFlags(&ov.s[l], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&ov.join[l], cudaEventDisableTiming) != cudaSuccess) return nullptr;
     }
@@ -74,7 +77,7 @@ FusedPlan fused_plan(long S, int ny, int nx, int N, long sub_req)
     t += 2 * align_up((size_t)p.sub * 4, 256) + 1024;       // decreasing, sorted, flag
     t += 9 * align_up((size_t)p.sub * N * 8, 256);          // contour-space temporaries
     t += align_up((size_t)p.sub * ny * 8, 256);             // Qref
-    t *= 2;                                                 // two passes in flight (one per internal stream)
+    t *= XC_LANES;                                          // passes in flight (one per internal stream)
     t += 2 * align_up((size_t)ny * 8, 256);                 // row metrics
     p.total = t + 8192;
     return p;
@@ -109,7 +112,7 @@ extern "C" int xc_keff_lwa_batch(const xc_keff_lwa_args* a, void* workspace, siz
     struct Lane {
         char *w_minmax, *w_hist; int32_t *sorted, *any_unsorted, *decr; double* edges;
         double *t_ctr, *t_area, *t_intg, *t_latEq, *t_Lmin, *t_dint, *t_dq, *t_Leq2, *t_nk, *t_Q;
-    } lanes[2];
+    } lanes[XC_LANES];
     for (Lane& L : lanes) {
         L.w_minmax = ar.take<char>(pl.ws_minmax);
         L.w_hist = ar.take<char>(pl.ws_hist);
@@ -144,7 +147,7 @@ extern "C" int xc_keff_lwa_batch(const xc_keff_lwa_args* a, void* workspace, siz
     if (!a->stage_ms && npass >= 2 && overlap_enabled()) ov = overlap_streams();
     if (ov) {
         XC_CUDA_OK(cudaEventRecord(ov->fork, st));
-        for (int l = 0; l < 2; ++l) XC_CUDA_OK(cudaStreamWaitEvent(ov->s[l], ov->fork, 0));
+        for (int l = 0; l < XC_LANES; ++l) XC_CUDA_OK(cudaStreamWaitEvent(ov->s[l], ov->fork, 0));
     }
     long pass = 0;
     auto mark = [&](int k) { if (a->stage_ms) cudaEventRecord(ev[(size_t)pass * (XC_N_STAGES + 1) + k], st); };
@@ -153,8 +156,8 @@ extern "C" int xc_keff_lwa_batch(const xc_keff_lwa_args* a, void* workspace, siz
 
     for (long s0 = 0; s0 < S; s0 += pl.sub) {
         const long ns = S - s0 < pl.sub ? S - s0 : pl.sub;
-        Lane& L = lanes[pass & 1];
-        void* ps = ov ? (void*)ov->s[pass & 1] : stream;              // this pass's stream
+        Lane& L = lanes[pass % XC_LANES];
+        void* ps = ov ? (void*)ov->s[pass % XC_LANES] : stream;              // this pass's stream
         auto at = [&](double* user, double* tmp) { return user ? user + s0 * (long)N : tmp; };
         const void* q = (const char*)a->q + (size_t)s0 * P * qsz;
         double* ctr = at(a->ctr, L.t_ctr);       double* area = at(a->area, L.t_area);
@@ -194,7 +197,7 @@ extern "C" int xc_keff_lwa_batch(const xc_keff_lwa_args* a, void* workspace, siz
         ++pass;
     }
     if (ov) {
-        for (int l = 0; l < 2; ++l) {
+        for (int l = 0; l < XC_LANES; ++l) {
             XC_CUDA_OK(cudaEventRecord(ov->join[l], ov->s[l]));
             XC_CUDA_OK(cudaStreamWaitEvent(st, ov->join[l], 0));
         }
