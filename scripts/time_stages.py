@@ -18,7 +18,7 @@ lam = torch.deg2rad(torch.tensor(lon, dtype=torch.float64, device="cuda"))[None,
 q = torch.empty((B, bench.NY, bench.NX), dtype=torch.float32, device="cuda")
 for s in range(B):
     q[s] = (torch.sin(phi) + 0.3 * torch.cos(phi) ** 2 * torch.sin(6 * lam + 3 * phi + s)).float() \
-        + 0.02 * torch.randn((bench.NY, bench.NX), generator=g, device="cuda")
+        + float(os.environ.get("XC_NOISE", "0.02")) * torch.randn((bench.NY, bench.NX), generator=g, device="cuda")
 out = plan.alloc_outputs(B)
 for _ in range(3):
     plan.run(q, out=out)

@@ -26,29 +26,6 @@ __device__ __forceinline__ double grad_s(const double* f, int k, int N, bool as_
     return interior ? __ddiv_rn(d, 2.0) : d;
 }
 
-// block-wide inclusive scan of pd[0..N) in place (256 threads)
-__device__ __forceinline__ void block_scan(double* pd, int N, double* wtot)
-{
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int L = (N + blockDim.x - 1) / blockDim.x;
-    const int r0 = tid * L, r1 = min(N, r0 + L);
-    double loc = 0.0;
-    for (int r = r0; r < r1; ++r) loc += pd[r];
-    double inc = loc;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        double t = __shfl_up_sync(XC_FULL, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) wtot[warp] = inc;
-    __syncthreads();
-    double carry = 0.0;
-    for (int w = 0; w < warp; ++w) carry += wtot[w];
-    double run = carry + (inc - loc);
-    for (int r = r0; r < r1; ++r) { run += pd[r]; pd[r] = run; }
-    __syncthreads();
-}
-
 struct EpiParams {
     const double* part; int C; int N; int lt;
     const int32_t* decreasing;
@@ -70,7 +47,6 @@ __global__ void __launch_bounds__(256) k_scan_epilogue(const EpiParams p)
     double* sl = sc + N;                            // latEq  [N]
     double* stab = sl + N;                          // A(Yeq) table       [n_table]
     double* scrd = stab + p.n_table;                // table coordinates  [n_table]
-    __shared__ double wtot[8];
     const long s = blockIdx.x;
     const int tid = threadIdx.x;
     const bool rev = p.decreasing && p.decreasing[s] != 0;
@@ -94,8 +70,12 @@ __global__ void __launch_bounds__(256) k_scan_epilogue(const EpiParams p)
     for (int n = tid; n < N; n += blockDim.x) sc[n] = p.ctr[s * N + n];
     for (int n = tid; n < p.n_table; n += blockDim.x) { stab[n] = p.table[n]; scrd[n] = p.table_coord[n]; }
     __syncthreads();
-    block_scan(sa, N, wtot);
-    block_scan(sg, N, wtot);
+    // sequential running sums, exactly np.cumsum's order (core.py:1320): empty bins
+    // leave the CDFs bit-for-bit flat (so d/dA sees exact zeros where the reference
+    // does); the two accumulators are scanned by two different warps at once
+    if (tid == 0)  { double run = 0.0; for (int r = 0; r < N; ++r) { run += sa[r]; sa[r] = run; } }
+    if (tid == 32) { double run = 0.0; for (int r = 0; r < N; ++r) { run += sg[r]; sg[r] = run; } }
+    __syncthreads();
     // cdf[-1] - cdf for the 'greater than' case (core.py:1322-1323), then the flip
     // that makes the contour index ascend (core.py:454-455) -- both in place
     const double ta = sa[N - 1], tg = sg[N - 1];

@@ -104,23 +104,44 @@ __device__ __forceinline__ void scatter_add4(double* H, uint8_t* tag, const int 
                                              const double (&w)[4][K], int lane)
 {
     if (MODE == HIST_MATCH) {
-        unsigned peers[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const bool a = bin[u] >= 0;
-            peers[u] = __match_any_sync(XC_FULL, a ? (unsigned)bin[u] : (0x80000000u | (unsigned)lane));
-            if (!a) peers[u] = 0u;
-        }
-        unsigned more;
-        do {
+            unsigned pr = __match_any_sync(XC_FULL, a ? (unsigned)bin[u] : (0x80000000u | (unsigned)lane));
+            if (!a) pr = 0u;
+            if (__reduce_max_sync(XC_FULL, __popc(pr)) <= 3) {
+                // few duplicates: the lowest remaining peer of every group adds, all clear that bit
+                do {
+                    if (pr && (__ffs(pr) - 1) == lane) rmw_add<K>(H + (size_t)bin[u] * K, w[u]);
+                    pr &= pr - 1u;
+                    __syncwarp();
+                } while (__any_sync(XC_FULL, pr != 0u));
+            } else {
+                // many lanes share a bin (smooth fields): combine them in registers first.
+                // The peers of a bin form a linked list in lane order; pointer jumping
+                // leaves the group total in the lowest lane after log2(group size) steps.
+                const unsigned above = (lane == 31) ? 0u : (pr & (0xffffffffu << (lane + 1)));
+                int nxt = above ? (__ffs(above) - 1) : -1;
+                const bool leader = a && ((__ffs(pr) - 1) == lane);
+                double acc[K];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (peers[u] && (__ffs(peers[u]) - 1) == lane) rmw_add<K>(H + (size_t)bin[u] * K, w[u]);
-                peers[u] &= peers[u] - 1u;
+                for (int k = 0; k < K; ++k) acc[k] = w[u][k];
+                while (__any_sync(XC_FULL, nxt >= 0)) {
+                    const int src = nxt >= 0 ? nxt : lane;
+                    double g[K];
+#pragma unroll
+                    for (int k = 0; k < K; ++k) g[k] = __shfl_sync(XC_FULL, acc[k], src);
+                    const int gn = __shfl_sync(XC_FULL, nxt, src);
+                    if (nxt >= 0) {
+#pragma unroll
+                        for (int k = 0; k < K; ++k) acc[k] += g[k];
+                        nxt = gn;
+                    }
+                }
+                if (leader) rmw_add<K>(H + (size_t)bin[u] * K, acc);
                 __syncwarp();
             }
-            more = peers[0] | peers[1] | peers[2] | peers[3];
-        } while (__any_sync(XC_FULL, more != 0u));
+        }
     } else if (MODE == HIST_TAG) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -333,10 +354,9 @@ k_reduce_scan(const double* __restrict__ part, int C, int K, int N, int scan_mod
 {
     extern __shared__ __align__(16) unsigned char smem[];
     double* pd = reinterpret_cast<double*>(smem);       // N values, scan order
-    __shared__ double wtot[8];
     __shared__ double total_s;
     const long s = blockIdx.x; const int k = blockIdx.y;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const bool rev = decreasing && decreasing[s] != 0;
     const bool suffix = scan_mode == XC_SCAN_SUFFIX;
 
@@ -357,23 +377,14 @@ k_reduce_scan(const double* __restrict__ part, int C, int K, int N, int scan_mod
         if (pdf) pdf[((size_t)s * K + k) * N + (rev ? N - 1 - n : n)] = acc;
     }
     __syncthreads();
-    const int L = (N + blockDim.x - 1) / blockDim.x;
-    const int r0 = tid * L, r1 = min(N, r0 + L);
-    double loc = 0.0;
-    for (int r = r0; r < r1; ++r) loc += pd[r];
-    // exclusive scan of the 256 thread totals
-    double inc = loc;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        double t = __shfl_up_sync(XC_FULL, inc, o);
-        if (lane >= o) inc += t;
+    // Sequential running sum, exactly np.cumsum's order (core.py:1320): empty bins
+    // leave the CDF bit-for-bit flat and the CDF of non-negative weights is monotone,
+    // which the d/dA step and check_mono rely on.  N additions by one thread cost a
+    // few microseconds; the parallelism of this kernel is across (slice, accumulator).
+    if (tid == 0) {
+        double run = 0.0;
+        for (int r = 0; r < N; ++r) { run += pd[r]; pd[r] = run; }
     }
-    if (lane == 31) wtot[warp] = inc;
-    __syncthreads();
-    double carry = 0.0;
-    for (int w = 0; w < warp; ++w) carry += wtot[w];
-    double run = carry + (inc - loc);
-    for (int r = r0; r < r1; ++r) { run += pd[r]; pd[r] = run; }
     __syncthreads();
     if (tid == 0) total_s = pd[N - 1];
     __syncthreads();

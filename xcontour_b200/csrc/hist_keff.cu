@@ -47,7 +47,7 @@ __device__ __forceinline__ int hk_find_bin(float vf, const double* e, int N, flo
     }
 }
 
-#ifndef XC_HK_DEDUP      /* 0: MATCH.ANY peel per item, 1: four MATCH.ANY issued up front, 2: byte tags */
+#ifndef XC_HK_DEDUP      /* 0: MATCH.ANY, peel or pointer jumping by duplicate count; 1: four MATCH.ANY up front; 2: byte tags; 4: peel only */
 #define XC_HK_DEDUP 0
 #endif
 
@@ -67,6 +67,32 @@ __device__ __forceinline__ unsigned hk_match(int bin, int lane)
     const bool a = bin >= 0;
     unsigned pr = __match_any_sync(XC_FULL, a ? (unsigned)bin : (0x80000000u | (unsigned)lane));
     return a ? pr : 0u;
+}
+// Heavy duplication (smooth fields: many lanes of a warp step share a bin) would
+// make the peel take one round per duplicate.  hk_jump combines the lanes that share
+// a bin BEFORE touching shared memory: the peers of a bin form a linked list in lane
+// order; pointer jumping (each lane adds the value of its successor and takes over
+// the successor's successor) leaves the group total in the lowest lane after
+// ceil(log2(group size)) shuffle steps, and that lane alone does one conflict-free
+// read-modify-write.  hk_scatter picks per warp step: peel for <= 3 duplicates,
+// pointer jumping beyond.
+__device__ __forceinline__ void hk_scatter(double2* H, int bin, double w0, double w1, int lane)
+{
+    const bool a = bin >= 0;
+    unsigned pr = hk_match(bin, lane);
+    const int cnt = __popc(pr);
+    if (__reduce_max_sync(XC_FULL, cnt) <= 3) { hk_peel(H, pr, bin, w0, w1, lane); return; }
+    const unsigned above = (lane == 31) ? 0u : (pr & (0xffffffffu << (lane + 1)));
+    int nxt = above ? (__ffs(above) - 1) : -1;
+    const bool leader = a && ((__ffs(pr) - 1) == lane);
+    while (__any_sync(XC_FULL, nxt >= 0)) {
+        const int src = nxt >= 0 ? nxt : lane;
+        const double g0 = __shfl_sync(XC_FULL, w0, src), g1 = __shfl_sync(XC_FULL, w1, src);
+        const int gn = __shfl_sync(XC_FULL, nxt, src);
+        if (nxt >= 0) { w0 += g0; w1 += g1; nxt = gn; }
+    }
+    if (leader) { double2 t = H[bin]; t.x += w0; t.y += w1; H[bin] = t; }
+    __syncwarp();
 }
 __device__ __forceinline__ void hk_tag(double2* H, uint8_t* tag, int bin, double w0, double w1, int lane)
 {
@@ -162,6 +188,11 @@ k_hist_keff(const HistKeffParams p)
         p0 = (p0 == p0) ? p0 : 0.0; p1 = (p1 == p1) ? p1 : 0.0;
         p2 = (p2 == p2) ? p2 : 0.0; p3 = (p3 == p3) ? p3 : 0.0;
 #if XC_HK_DEDUP == 0
+        hk_scatter(Hw, b0, a0, p0, lane);
+        hk_scatter(Hw, b1, a1, p1, lane);
+        hk_scatter(Hw, b2, a2, p2, lane);
+        hk_scatter(Hw, b3, a3, p3, lane);
+#elif XC_HK_DEDUP == 4
         hk_peel(Hw, hk_match(b0, lane), b0, a0, p0, lane);
         hk_peel(Hw, hk_match(b1, lane), b1, a1, p1, lane);
         hk_peel(Hw, hk_match(b2, lane), b2, a2, p2, lane);
