@@ -19,6 +19,8 @@ q = torch.empty((B, bench.NY, bench.NX), dtype=torch.float32, device="cuda")
 for s in range(B):
     q[s] = (torch.sin(phi) + 0.3 * torch.cos(phi) ** 2 * torch.sin(6 * lam + 3 * phi + s)).float() \
         + float(os.environ.get("XC_NOISE", "0.02")) * torch.randn((bench.NY, bench.NX), generator=g, device="cuda")
+if os.environ.get("XC_QUANT"):      # pathological: large patches of identical values
+    k = float(os.environ["XC_QUANT"]); q = torch.round(q * k) / k
 out = plan.alloc_outputs(B)
 for _ in range(3):
     plan.run(q, out=out)
