@@ -752,3 +752,21 @@ def test_contour2d_1d_area_explicit_levels_check_mono(ops, vort):
                        check_mono=True)
     with pytest.raises(Exception, match="not monotonic var"):
         an2.cal_integral_within_contours_hist(an2.cal_contours(4001))
+
+
+@pytest.mark.parametrize("env", [
+    {"XCB200_LWA_HEAVY": "3"},                                   # register pre-reduction in the LWA scatter
+    {"XCB200_LWA_DEDUP": "m"},                                   # MATCH.ANY peel in the LWA scatter
+    {"XCB200_HIST_DEDUP": "t", "XCB200_NO_HIST_KEFF": "1"},      # byte tags in the general binning kernel
+    {"XCB200_NO_HIST_KEFF": "1", "XCB200_OVERLAP": "0"},         # general binning kernel, serial schedule
+    {"XCB200_SUB_BATCH": "1"},                                   # one slice per pass, two passes in flight
+])
+def test_alternate_code_paths_smoke(ops, env):
+    """The run-time selectable variants (read once per process from the environment)
+    each pass the oracle-checked smoke run in a fresh process."""
+    import subprocess, sys
+    from conftest import ROOT
+    e = dict(os.environ, **env)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "__graft_entry__.py"), "--smoke-only"],
+                       env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "smoke ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
