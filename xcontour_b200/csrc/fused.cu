@@ -77,6 +77,7 @@ FusedPlan fused_plan(long S, int ny, int nx, int N, long sub_req)
     t += 2 * align_up((size_t)p.sub * 4, 256) + 1024;       // decreasing, sorted, flag
     t += 9 * align_up((size_t)p.sub * N * 8, 256);          // contour-space temporaries
     t += align_up((size_t)p.sub * ny * 8, 256);             // Qref
+    t += align_up((size_t)p.sub * 16, 256) + align_up(lwa_scratch_doubles(p.sub, true) * 8, 256);   // (min, max), LWA scratch
     t *= XC_LANES;                                          // passes in flight (one per internal stream)
     t += 2 * align_up((size_t)ny * 8, 256);                 // row metrics
     p.total = t + 8192;
@@ -110,7 +111,7 @@ extern "C" int xc_keff_lwa_batch(const xc_keff_lwa_args* a, void* workspace, siz
                ws_bytes, pl.total);
     Arena ar(workspace, ws_bytes);
     struct Lane {
-        char *w_minmax, *w_hist; int32_t *sorted, *any_unsorted, *decr; double* edges;
+        char *w_minmax, *w_hist; int32_t *sorted, *any_unsorted, *decr; double *edges, *minmax, *lwa_scratch;
         double *t_ctr, *t_area, *t_intg, *t_latEq, *t_Lmin, *t_dint, *t_dq, *t_Leq2, *t_nk, *t_Q;
     } lanes[XC_LANES];
     for (Lane& L : lanes) {
@@ -120,6 +121,8 @@ extern "C" int xc_keff_lwa_batch(const xc_keff_lwa_args* a, void* workspace, siz
         L.any_unsorted = ar.take<int32_t>(1);
         L.edges = ar.take<double>((size_t)pl.sub * (N + 1));
         L.decr = ar.take<int32_t>((size_t)pl.sub);
+        L.minmax = ar.take<double>((size_t)pl.sub * 2);
+        L.lwa_scratch = ar.take<double>(lwa_scratch_doubles(pl.sub, true));
         L.t_ctr = ar.take<double>((size_t)pl.sub * N);   L.t_area = ar.take<double>((size_t)pl.sub * N);
         L.t_intg = ar.take<double>((size_t)pl.sub * N);  L.t_latEq = ar.take<double>((size_t)pl.sub * N);
         L.t_Lmin = ar.take<double>((size_t)pl.sub * N);  L.t_dint = ar.take<double>((size_t)pl.sub * N);
@@ -169,7 +172,7 @@ extern "C" int xc_keff_lwa_batch(const xc_keff_lwa_args* a, void* workspace, siz
 
         mark(0);
         // (1)+(1b) min/max, levels and per-'time'-branch edges in two launches
-        if (minmax_levels_impl(q, a->q_dtype, ns, P, N, a->increase, a->ctr_dtype, ctr, nullptr,
+        if (minmax_levels_impl(q, a->q_dtype, ns, P, N, a->increase, a->ctr_dtype, ctr, L.minmax,
                                L.edges, L.decr, L.any_unsorted, L.w_minmax, pl.ws_minmax, ps)) return 1;
         mark(1);
         mark(2);
@@ -192,7 +195,7 @@ extern "C" int xc_keff_lwa_batch(const xc_keff_lwa_args* a, void* workspace, siz
         // (6) LWA
         if (a->lwa)
             if (lwa_impl(q, a->q_dtype, ns, ny, nx, Qref, a->ww, a->increase, a->part, 1,
-                         a->lwa + (size_t)s0 * P, L.sorted, L.any_unsorted, true, ps)) return 1;
+                         a->lwa + (size_t)s0 * P, L.sorted, L.any_unsorted, true, L.minmax, L.lwa_scratch, ps)) return 1;
         mark(5);
         ++pass;
     }

@@ -49,8 +49,13 @@ int minmax_levels_impl(const void* q, int q_dtype, long S, long P, int N, int in
                        int32_t* flag_to_clear, void* workspace, size_t ws_bytes, void* stream);
 
 // LWA with sortedness flags already on the device (fused path)
+// minmax: NaN-skipping (min, max) per slice [S][2] if the caller has them (else they are
+// computed into `scratch`); scratch: lwa_scratch_doubles(S, minmax != nullptr) doubles.
+// The fixed-point kernel hands slices with non-finite values to the exact loop by
+// clearing sorted[s] and raising *any_unsorted.
+size_t lwa_scratch_doubles(long S, bool have_minmax);
 int lwa_impl(const void* q, int q_dtype, long S, int n_eq, int n_x, const double* Qref, const double* ww,
              int increase, int part, int variant, double* out, int32_t* sorted,
-             const int32_t* any_unsorted, bool flags_ready, void* stream);
+             int32_t* any_unsorted, bool flags_ready, const double* minmax, double* scratch, void* stream);
 
 }  // namespace xc

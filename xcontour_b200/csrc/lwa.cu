@@ -351,6 +351,315 @@ k_lwa_fast(const QT* __restrict__ q, long s0, int ny, int nx,
     }
 }
 
+// ---------------------------------------------------------------------------
+// Fixed-point variant of the fast kernel (default).  Measured on B200
+// (scripts/micro/atoms_bench.cu): a native shared-memory integer atomic
+// (ATOMS.ADD.U32) costs 2.6-3.4 cycles per warp instruction, a 64-bit add built
+// from two of them plus a carry 4.3-5.0, against 15-18.5 for ONE conflict-free
+// read-modify-write round of an fp64 pair (and 2.4 election rounds on average in
+// k_lwa_fast).  So the difference arrays become 64-bit two's-complement integers:
+//     X_S = rn(w * 2^kS),   X_V = rn(w * (v - c) * 2^kV)
+// with c the mid-range of the slice and kS, kV chosen per slice so that a column
+// of n_eq terms cannot overflow 63 bits (|X| < 2^(62 - ceil(log2(n_eq+1))): 52
+// significant bits at n_eq = 721, i.e. the resolution of the largest term's own
+// fp64 ulp).  Integer adds are exact and order-independent, so
+//   * any thread may deposit into any slot of its column tile: lanes run along
+//     x (coalesced loads, no transposed staging), there is no lane election, no
+//     warp-private array, and a CTA has as many warps as registers allow;
+//   * the +X deposit at slot j'+1 never touches shared memory: the prefix pass
+//     re-derives it from (q, ww) with the same rounding, and an inactive cell
+//     deposits -X at j'+1, which cancels exactly;
+//   * results are bit-reproducible whatever the schedule.
+//   LWA[j] = sg * ( V_j 2^-kV - (Q_j - c) * S_j 2^-kS ).
+// grid = (ceil(n_x / 8), slices); block = FX_NT threads = (column c, row segment).
+// Shared memory: four u32 planes [slot][column] (lo/hi words of S and V), Q, a
+// 1024-bucket LUT over Q and the per-segment totals of the block scan.
+constexpr int FX_TC  = 8;
+constexpr int FX_NT  = 512;
+constexpr int FX_SEG = FX_NT / FX_TC;      // row segments per column
+constexpr int FX_LUT = 1024;
+constexpr int FX_TOTP = FX_SEG + 2;        // padded row of the totals table
+
+struct LwaFxSmem { size_t off_Q, off_far, off_lut, off_tot, total; int plane; };
+static __host__ __device__ inline LwaFxSmem lwa_fx_layout(int ny)
+{
+    LwaFxSmem L;
+    L.plane = ((ny + 1) * FX_TC + 3) & ~3;                       // u32 words per plane
+    size_t o = 0;
+    L.off_Q = o;   o += (size_t)((ny + 1) & ~1) * 8;
+    L.off_far = o; o += (size_t)4 * L.plane * 4;
+    L.off_lut = o; o += (size_t)FX_LUT * 4;
+    L.off_tot = o; o += (size_t)2 * FX_TC * FX_TOTP * 8;
+    L.total = o;
+    return L;
+}
+
+__device__ __forceinline__ int fx_bucket(float vf, float qminf, float scalef)
+{
+    const float t = fminf(fmaxf((vf - qminf) * scalef, 0.0f), (float)(FX_LUT - 1));
+    return __float2int_rz(t);
+}
+
+// 64-bit two's-complement add into (lo[idx], hi[idx]) with two native 32-bit
+// shared atomics; the carry out of the low word is decided by the value the low
+// word held when THIS add reached it, so the pair ends up as the exact sum modulo
+// 2^64 in any interleaving.
+__device__ __forceinline__ void fx_add64(uint32_t* lo, uint32_t* hi, int idx, long long x)
+{
+    const uint32_t xl = (uint32_t)x, xh = (uint32_t)((unsigned long long)x >> 32);
+    const uint32_t old = atomicAdd(lo + idx, xl);
+    const uint32_t carry = (uint32_t)((old + xl) < xl);
+    atomicAdd(hi + idx, xh + carry);
+}
+
+// Per-slice preparation (one CTA per slice): the fixed-point scales from the
+// NaN-skipping (min, max) of the slice and max |ww|, and the LUT over Q
+// (first row whose bucket is >= b, packed (first[b], first[b+1])), both shared by
+// every column tile of the slice.  A slice with an infinite value is handed to the
+// exact loop (sorted[s] = 0, *any_unsorted = 1).
+constexpr int FX_PREP_NT = 256;
+struct FxScale { double c, sS, sV, iS, iV, pad0, pad1, pad2; };
+
+__global__ void __launch_bounds__(FX_PREP_NT)
+k_lwa_fx_prep(long s0, int ny, const double* __restrict__ Qref, int increase,
+              int32_t* sorted, int32_t* any_unsorted,
+              const double* __restrict__ rng, int rngC, const double* __restrict__ wmax_part, int n_wmax,
+              FxScale* __restrict__ fxs, uint32_t* __restrict__ lutg)
+{
+    const long s = s0 + blockIdx.x;
+    if (!sorted[s]) return;
+    __shared__ uint16_t first[FX_LUT + 2];
+    __shared__ double swm[FX_PREP_NT / 32];
+    const int tid = threadIdx.x;
+    const double sg = increase ? 1.0 : -1.0;
+    const double* Qg = Qref + s * (long)ny;
+    double wm = 0.0;
+    for (int k = tid; k < n_wmax; k += FX_PREP_NT) wm = fmax(wm, wmax_part[k]);
+    wm = warp_max(wm);
+    if ((tid & 31) == 0) swm[tid >> 5] = wm;
+    const double qmin = sg * Qg[0], qmax = sg * Qg[ny - 1];
+    const float qminf = (float)qmin;
+    const float scalef = (qmax > qmin) ? (float)((double)FX_LUT / (qmax - qmin)) : 0.0f;
+    for (int j = tid; j <= ny; j += FX_PREP_NT) {
+        const int bj = (j < ny) ? fx_bucket((float)(sg * Qg[j]), qminf, scalef) : FX_LUT;
+        const int bp = (j > 0) ? fx_bucket((float)(sg * Qg[j - 1]), qminf, scalef) : -1;
+        for (int b = bp + 1; b <= bj; ++b) first[b] = (uint16_t)j;
+    }
+    __syncthreads();
+    uint32_t* lut = lutg + (size_t)blockIdx.x * FX_LUT;
+    for (int b = tid; b < FX_LUT; b += FX_PREP_NT) lut[b] = (uint32_t)first[b] | ((uint32_t)first[b + 1] << 16);
+    if (tid == 0) {
+        for (int k = 1; k < FX_PREP_NT / 32; ++k) wm = fmax(wm, swm[k]);
+        double lo = CUDART_INF, hi = -CUDART_INF;
+        for (int k = 0; k < rngC; ++k) {
+            lo = fmin(lo, rng[(s * rngC + k) * 2]); hi = fmax(hi, rng[(s * rngC + k) * 2 + 1]);
+        }
+        const double a = sg * lo, b = sg * hi;
+        const double vlo = fmin(a, b), vhi = fmax(a, b);
+        FxScale f;
+        f.c = 0.5 * vlo + 0.5 * vhi;
+        const double vabs = fmax(vhi - f.c, f.c - vlo);
+        const double MV = wm * vabs * 1.0000001, MS = wm;
+        const bool empty = !(lo <= hi);                              // slice without a finite value
+        if (!empty && !(isfinite(MV) && isfinite(MS) && isfinite(f.c))) {  // inf in q or ww: exact loop instead
+            sorted[s] = 0; if (any_unsorted) *any_unsorted = 1;
+        }
+        int hb = 1; while ((1 << hb) < ny + 1) ++hb;                 // sums of up to ny terms
+        const int kS = (MS > 0.0 && isfinite(MS) && !empty) ? 61 - hb - ilogb(MS) : 0;
+        const int kV = (MV > 0.0 && isfinite(MV) && !empty) ? 61 - hb - ilogb(MV) : 0;
+        if (empty || !isfinite(f.c)) f.c = 0.0;
+        f.sS = scalbn(1.0, kS); f.iS = scalbn(1.0, -kS);
+        f.sV = scalbn(1.0, kV); f.iV = scalbn(1.0, -kV);
+        f.pad0 = f.pad1 = f.pad2 = 0.0;
+        fxs[blockIdx.x] = f;
+    }
+}
+
+// the deposit of one cell; used by the scatter phase and re-derived (bit for bit)
+// by the prefix phase
+__device__ __forceinline__ bool fx_terms(double v, double w, double c, double sS, double sV, long long& XS, long long& XV)
+{
+    const bool valid = (v == v) && (w == w);
+    XS = valid ? __double2ll_rn(__dmul_rn(w, sS)) : 0ll;
+    XV = valid ? __double2ll_rn(__dmul_rn(__dmul_rn(w, __dsub_rn(v, c)), sV)) : 0ll;
+    return valid;
+}
+
+constexpr int FX_U = 4;              // rows whose loads are in flight together
+
+template <typename QT>
+__global__ void __launch_bounds__(FX_NT, 2)
+k_lwa_fx(const QT* __restrict__ q, long s0, long sbase, int ny, int nx,
+         const double* __restrict__ Qref, const double* __restrict__ ww,
+         int increase, int part, const int32_t* __restrict__ sorted,
+         const FxScale* __restrict__ fxs, const uint32_t* __restrict__ lutg,
+         int Lseg, double* __restrict__ out)
+{
+    const long s = s0 + blockIdx.y;
+    if (!sorted[s]) return;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const LwaFxSmem L = lwa_fx_layout(ny);
+    double*    Qs  = reinterpret_cast<double*>(smem + L.off_Q);
+    uint32_t*  far = reinterpret_cast<uint32_t*>(smem + L.off_far);
+    uint32_t*  lut = reinterpret_cast<uint32_t*>(smem + L.off_lut);
+    long long* tot = reinterpret_cast<long long*>(smem + L.off_tot);     // [2][FX_TC][FX_TOTP]
+    uint32_t *Slo = far, *Shi = far + L.plane, *Vlo = far + 2 * L.plane, *Vhi = far + 3 * L.plane;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double sg = increase ? 1.0 : -1.0;
+    const double* Qg = Qref + s * (long)ny;
+    const uint32_t* lg = lutg + (size_t)(s - sbase) * FX_LUT;
+    for (int j = tid; j < ny; j += FX_NT) Qs[j] = sg * Qg[j];
+#pragma unroll
+    for (int k = 0; k < FX_LUT / FX_NT; ++k) lut[tid + k * FX_NT] = __ldg(lg + tid + k * FX_NT);
+    {
+        uint4* z = reinterpret_cast<uint4*>(far);
+        for (int k = tid; k < L.plane; k += FX_NT) z[k] = make_uint4(0u, 0u, 0u, 0u);   // 4 planes of L.plane words
+    }
+    const FxScale* fp = fxs + (s - sbase);
+    const double fc = __ldg(&fp->c), fsS = __ldg(&fp->sS), fsV = __ldg(&fp->sV);
+    __syncthreads();
+    const double qmin = Qs[0], qmax = Qs[ny - 1];
+    const float qminf = (float)qmin;
+    const float scalef = (qmax > qmin) ? (float)((double)FX_LUT / (qmax - qmin)) : 0.0f;
+
+    const bool keep_pos = (part == XC_PART_UPPER) == (increase != 0);
+    const bool use_t1 = (part == XC_PART_ALL) || !keep_pos;   // mask -1 region
+    const bool use_t2 = (part == XC_PART_ALL) || keep_pos;    // mask +1 region
+
+    const int c = tid & (FX_TC - 1), seg = tid / FX_TC;
+    const int i = blockIdx.x * FX_TC + c;
+    const bool col_ok = i < nx;
+    const int r0 = min(ny, seg * Lseg), r1 = min(ny, r0 + Lseg);
+    const QT* qc = q + s * (long)ny * nx + i;
+    const double* wc = ww + i;
+
+    // ---- scatter: one deposit of -X at the far end of each cell's range ----
+    long long ownS = 0, ownV = 0;
+    if (col_ok) {
+        for (int jb = r0; jb < r1; jb += FX_U) {
+            QT qv[FX_U]; double wv[FX_U];
+#pragma unroll
+            for (int u = 0; u < FX_U; ++u) {
+                const int jp = min(jb + u, r1 - 1);
+                qv[u] = __ldg(qc + (long)jp * nx); wv[u] = __ldg(wc + (long)jp * nx);
+            }
+#pragma unroll
+            for (int u = 0; u < FX_U; ++u) {
+                const int jp = jb + u;
+                if (jp >= r1) break;
+                const double v = sg * (double)qv[u];
+                long long XS, XV;
+                if (!fx_terms(v, wv[u], fc, fsS, fsV, XS, XV)) continue;
+                const uint32_t pk = lut[fx_bucket((float)v, qminf, scalef)];
+                int x = (int)(pk & 0xffffu), e = (int)(pk >> 16);
+                const int e0 = e;                                    // rows >= e0 have Q > v
+                while (x < e) { const int mid = (x + e) >> 1; if (Qs[mid] < v) x = mid + 1; else e = mid; }
+                int target = jp + 1;                                 // inactive: cancels the own deposit
+                if (x > jp + 1) { if (use_t1) target = x; }          // x = #{Q < v}
+                else {
+                    int h = x;                                       // #{Q <= v}; ties live in v's bucket only
+                    if (h < e0 && Qs[h] == v) {
+                        int y = e0; ++h;
+                        while (h < y) { const int mid = (h + y) >> 1; if (Qs[mid] <= v) h = mid + 1; else y = mid; }
+                    }
+                    if (h <= jp && use_t2) target = h;
+                }
+                ownS += XS; ownV += XV;
+                const int idx = target * FX_TC + c;
+                fx_add64(Slo, Shi, idx, -XS);
+                fx_add64(Vlo, Vhi, idx, -XV);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- prefix down the columns: segment totals, block scan, final walk ----
+    {
+        unsigned long long aSl = 0, aVl = 0; long long aSh = 0, aVh = 0;
+        for (int j = r0; j < r1; ++j) {
+            const int idx = j * FX_TC + c;
+            aSl += Slo[idx]; aSh += (int32_t)Shi[idx]; aVl += Vlo[idx]; aVh += (int32_t)Vhi[idx];
+        }
+        tot[c * FX_TOTP + seg] = (long long)aSl + (aSh << 32) + ownS;
+        tot[(FX_TC + c) * FX_TOTP + seg] = (long long)aVl + (aVh << 32) + ownV;
+    }
+    __syncthreads();
+    if (warp < 2 * FX_TC) {                                      // warp = (which, column): exclusive scan over segments
+        long long* row = tot + (size_t)warp * FX_TOTP;
+        const long long a0 = row[2 * lane], a1 = row[2 * lane + 1];
+        long long x = a0 + a1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(XC_FULL, x, o); if (lane >= o) x += t; }
+        const long long ex = x - (a0 + a1);
+        row[2 * lane] = ex; row[2 * lane + 1] = ex + a0;
+    }
+    __syncthreads();
+    if (col_ok) {
+        const double fiS = __ldg(&fp->iS), fiV = __ldg(&fp->iV);
+        long long RS = tot[c * FX_TOTP + seg], RV = tot[(FX_TC + c) * FX_TOTP + seg];
+        double* oc = out + s * (long)ny * nx + i;
+        for (int jb = r0; jb < r1; jb += FX_U) {
+            QT qv[FX_U]; double wv[FX_U];
+#pragma unroll
+            for (int u = 0; u < FX_U; ++u) {
+                const int j = min(jb + u, r1 - 1);
+                qv[u] = __ldg(qc + (long)j * nx); wv[u] = __ldg(wc + (long)j * nx);
+            }
+#pragma unroll
+            for (int u = 0; u < FX_U; ++u) {
+                const int j = jb + u;
+                if (j >= r1) break;
+                const int idx = j * FX_TC + c;
+                RS += (long long)(((unsigned long long)Shi[idx] << 32) | Slo[idx]);
+                RV += (long long)(((unsigned long long)Vhi[idx] << 32) | Vlo[idx]);
+                const double Sj = __dmul_rn((double)RS, fiS), Vj = __dmul_rn((double)RV, fiV);
+                oc[(long)j * nx] = sg * (Vj - (Qs[j] - fc) * Sj);
+                long long XS, XV;
+                fx_terms(sg * (double)qv[u], wv[u], fc, fsS, fsV, XS, XV);
+                RS += XS; RV += XV;
+            }
+        }
+    }
+}
+
+// NaN-skipping (min, max) of every slice in rngC partials (stand-alone xc_lwa; the
+// fused batch already has them from the levels stage) and max |ww|
+template <typename QT>
+__global__ void k_lwa_range(const QT* __restrict__ q, long P, int C, double* __restrict__ rng)
+{
+    const long s = blockIdx.y;
+    const QT* qs = q + s * P;
+    const long per = (P + C - 1) / C, beg = blockIdx.x * per, end = min(P, beg + per);
+    double lo = CUDART_INF, hi = -CUDART_INF;
+    for (long k = beg + threadIdx.x; k < end; k += blockDim.x) {
+        const double v = (double)__ldg(qs + k);
+        lo = fmin(lo, v); hi = fmax(hi, v);                      // fmin/fmax skip NaN
+    }
+    lo = warp_min(lo); hi = warp_max(hi);
+    __shared__ double sl[8], sh[8];
+    if ((threadIdx.x & 31) == 0) { sl[threadIdx.x >> 5] = lo; sh[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) { lo = fmin(lo, sl[k]); hi = fmax(hi, sh[k]); }
+        rng[(s * C + blockIdx.x) * 2] = lo; rng[(s * C + blockIdx.x) * 2 + 1] = hi;
+    }
+}
+__global__ void k_absmax_partial(const double* __restrict__ x, long P, double* __restrict__ part)
+{
+    double mx = 0.0;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < P; i += (long)gridDim.x * blockDim.x)
+        mx = fmax(mx, fabs(x[i]));
+    mx = warp_max(mx);
+    __shared__ double sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) mx = fmax(mx, sm[k]);
+        part[blockIdx.x] = mx;
+    }
+}
+
 // Variant 2 (cal_local_wave_activity2, core.py:802-905: the point is fixed, the
 // profile varies).  With a sorted profile it needs no scatter at all:
 //   out[j] = sg * ( [hi<j] (v (W_j - W_hi) - (QW_j - QW_hi))  -  [lo>j] (v (W_lo - W_j) - (QW_lo - QW_j)) )
@@ -609,7 +918,20 @@ extern "C" int xc_lwa_weights(const void* dA, int dA_dtype, long P, double* ww,
     return 0;
 }
 
-extern "C" size_t xc_lwa_workspace_bytes(long S) { return 256 + (size_t)(S > 0 ? S : 0) * sizeof(int32_t); }
+constexpr int LWA_RNG_C = 8;        // partial (min, max) CTAs per slice in the stand-alone path
+constexpr int LWA_WMAX_N = 128;     // partial max |ww| CTAs
+constexpr long FX_CHUNK = 1024;     // slices per fixed-point launch (bounds the per-slice LUT scratch)
+size_t xc::lwa_scratch_doubles(long S, bool have_minmax)
+{
+    const long Sp = S > 0 ? S : 0, ch = Sp < FX_CHUNK ? Sp : FX_CHUNK;
+    return (size_t)LWA_WMAX_N + 32 + (have_minmax ? 0 : (size_t)Sp * LWA_RNG_C * 2) +
+           (size_t)ch * (sizeof(FxScale) / 8 + FX_LUT / 2) + 64;
+}
+
+extern "C" size_t xc_lwa_workspace_bytes(long S)
+{
+    return 1024 + (size_t)(S > 0 ? S : 0) * sizeof(int32_t) + lwa_scratch_doubles(S, false) * sizeof(double);
+}
 
 extern "C" int xc_lwa(const void* q, int q_dtype, long S, int n_eq, int n_x,
                       const double* Qref, const double* ww,
@@ -618,14 +940,24 @@ extern "C" int xc_lwa(const void* q, int q_dtype, long S, int n_eq, int n_x,
 {
     XC_REQUIRE(workspace && ws_bytes >= xc_lwa_workspace_bytes(S), "xc_lwa: workspace too small");
     Arena ar(workspace, ws_bytes);
-    int32_t* sorted = ar.take<int32_t>((size_t)S);
+    int32_t* sorted = ar.take<int32_t>((size_t)(S > 0 ? S : 0));
+    double* scratch = ar.take<double>(lwa_scratch_doubles(S, false));
     return lwa_impl(q, q_dtype, S, n_eq, n_x, Qref, ww, increase, part, variant, out, sorted,
-                    nullptr, false, stream);
+                    nullptr, false, nullptr, scratch, stream);
+}
+
+// XCB200_LWA_FX=0 selects the fp64 read-modify-write kernel (k_lwa_fast) instead of
+// the fixed-point one (kept for A/B timing and as a cross-check in the tests).
+static bool lwa_use_fx()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("XCB200_LWA_FX"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
 }
 
 int xc::lwa_impl(const void* q, int q_dtype, long S, int n_eq, int n_x, const double* Qref, const double* ww,
                  int increase, int part, int variant, double* out, int32_t* sorted,
-                 const int32_t* any_unsorted, bool flags_ready, void* stream)
+                 int32_t* any_unsorted, bool flags_ready, const double* minmax, double* scratch, void* stream)
 {
     XC_REQUIRE(q && Qref && ww && out, "xc_lwa: null pointer");
     XC_REQUIRE(S > 0 && n_eq >= 1 && n_x >= 1, "xc_lwa: need S>0, n_eq>=1, n_x>=1");
@@ -637,12 +969,53 @@ int xc::lwa_impl(const void* q, int q_dtype, long S, int n_eq, int n_x, const do
     const bool match = lwa_use_match();
     const int qbytes = q_dtype == XC_F32 ? 4 : 8;
     const int tc = (n_eq < 65535) ? lwa_pick_tc(n_eq, qbytes, !match) : 0;
-    const bool fast = (variant == 1) && tc >= 1 && (size_t)tc * (n_eq + 2) * 16 >= (size_t)(LWA_LUT + 1) * 2;
-    if (fast) {
-        if (!flags_ready) {
-            k_check_sorted<<<(unsigned)S, 256, 0, st>>>(Qref, n_eq, increase, sorted);
+    const LwaFxSmem FL = lwa_fx_layout(n_eq);
+    const bool fx = (variant == 1) && lwa_use_fx() && scratch && n_eq < 65535 && FL.total <= 227 * 1024 &&
+                    FX_LUT % FX_NT == 0;
+    const bool fast = fx || ((variant == 1) && tc >= 1 && (size_t)tc * (n_eq + 2) * 16 >= (size_t)(LWA_LUT + 1) * 2);
+    if (fast && !flags_ready) {
+        k_check_sorted<<<(unsigned)S, 256, 0, st>>>(Qref, n_eq, increase, sorted);
+        XC_LAUNCH_OK();
+    }
+    if (fx) {
+        const long P = (long)n_eq * n_x;
+        double* wpart = scratch;
+        const double* rng = minmax; int rngC = 1;
+        if (!rng) {
+            double* r = scratch + LWA_WMAX_N + 32; rng = r; rngC = LWA_RNG_C;
+            for (long s0 = 0; s0 < S; s0 += 65535) {
+                const long ns = S - s0 < 65535 ? S - s0 : 65535;
+                dim3 grid(LWA_RNG_C, (unsigned)ns);
+                if (q_dtype == XC_F32) k_lwa_range<float><<<grid, 256, 0, st>>>((const float*)q + s0 * P, P, LWA_RNG_C, r + s0 * LWA_RNG_C * 2);
+                else                   k_lwa_range<double><<<grid, 256, 0, st>>>((const double*)q + s0 * P, P, LWA_RNG_C, r + s0 * LWA_RNG_C * 2);
+                XC_LAUNCH_OK();
+            }
+        }
+        k_absmax_partial<<<LWA_WMAX_N, 256, 0, st>>>(ww, P, wpart);
+        XC_LAUNCH_OK();
+        char* cur = reinterpret_cast<char*>(scratch + LWA_WMAX_N + 32 + (minmax ? 0 : (size_t)S * LWA_RNG_C * 2));
+        cur = reinterpret_cast<char*>(align_up((size_t)cur, 64));
+        FxScale* fxs = reinterpret_cast<FxScale*>(cur);
+        const long ch = S < FX_CHUNK ? S : FX_CHUNK;
+        uint32_t* lutg = reinterpret_cast<uint32_t*>(cur + (size_t)ch * sizeof(FxScale));
+        int Lseg = (n_eq + FX_SEG - 1) / FX_SEG; Lseg |= 1;       // odd: conflict-free column walks
+        if (q_dtype == XC_F32) XC_CUDA_OK(cudaFuncSetAttribute(k_lwa_fx<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL.total));
+        else                   XC_CUDA_OK(cudaFuncSetAttribute(k_lwa_fx<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL.total));
+        for (long s0 = 0; s0 < S; s0 += FX_CHUNK) {
+            const long ns = S - s0 < FX_CHUNK ? S - s0 : FX_CHUNK;
+            k_lwa_fx_prep<<<(unsigned)ns, FX_PREP_NT, 0, st>>>(s0, n_eq, Qref, increase, sorted, any_unsorted,
+                                                               rng, rngC, wpart, LWA_WMAX_N, fxs, lutg);
+            XC_LAUNCH_OK();
+            dim3 grid((unsigned)((n_x + FX_TC - 1) / FX_TC), (unsigned)ns);
+            if (q_dtype == XC_F32)
+                k_lwa_fx<float><<<grid, FX_NT, FL.total, st>>>((const float*)q, s0, s0, n_eq, n_x, Qref, ww, increase, part, sorted,
+                                                              fxs, lutg, Lseg, out);
+            else
+                k_lwa_fx<double><<<grid, FX_NT, FL.total, st>>>((const double*)q, s0, s0, n_eq, n_x, Qref, ww, increase, part, sorted,
+                                                               fxs, lutg, Lseg, out);
             XC_LAUNCH_OK();
         }
+    } else if (fast) {
         int rc;
         if (q_dtype == XC_F32)
             rc = match ? launch_lwa_fast<float, true>((const float*)q, S, n_eq, n_x, Qref, ww, increase, part, sorted, out, tc, st)
