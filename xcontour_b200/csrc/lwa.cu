@@ -360,7 +360,7 @@ k_lwa_fast(const QT* __restrict__ q, long s0, int ny, int nx,
 // k_lwa_fast).  So the difference arrays become 64-bit two's-complement integers:
 //     X_S = rn(w * 2^kS),   X_V = rn(w * (v - c) * 2^kV)
 // with c the mid-range of the slice and kS, kV chosen per slice so that a column
-// of n_eq terms cannot overflow 63 bits (|X| < 2^(62 - ceil(log2(n_eq+1))): 52
+// of n_eq terms cannot overflow 63 bits (|X| < 2^min(51, 62 - ceil(log2(n_eq+1))): 51
 // significant bits at n_eq = 721, i.e. the resolution of the largest term's own
 // fp64 ulp).  Integer adds are exact and order-independent, so
 //   * any thread may deposit into any slot of its column tile: lanes run along
@@ -394,10 +394,26 @@ static __host__ __device__ inline LwaFxSmem lwa_fx_layout(int ny)
     return L;
 }
 
+// The conversion instructions (F2I / I2F / F2F with a 64-bit side) run on the XU
+// pipe at a fraction of the ALU rate and were what bound the first version of this
+// kernel; the conversions below use the classic magic-number forms on the FMA /
+// fp64 / integer pipes instead (scripts/micro/cvt_bench.cu).
 __device__ __forceinline__ int fx_bucket(float vf, float qminf, float scalef)
 {
     const float t = fminf(fmaxf((vf - qminf) * scalef, 0.0f), (float)(FX_LUT - 1));
-    return __float2int_rz(t);
+    return __float_as_int(t + 12582912.0f) - 0x4B400000;        // rn(t), 0 <= t <= 1023; monotone like the rz form
+}
+// rn(x) for |x| <= 2^51 (round to nearest even, like __double2ll_rn)
+__device__ __forceinline__ long long fx_rn(double x)
+{
+    return __double_as_longlong(__dadd_rn(x, 6755399441055744.0)) - 0x4338000000000000ll;   // 1.5 * 2^52
+}
+// (double)r, correctly rounded, for any 64-bit r
+__device__ __forceinline__ double fx_to_double(long long r)
+{
+    const double dlo = __hiloint2double(0x43300000, (int)(uint32_t)r) - 4503599627370496.0;                    // 2^52
+    const double dhi = __hiloint2double(0x43300000, (int)((uint32_t)(r >> 32) ^ 0x80000000u)) - 4503601774854144.0; // 2^52 + 2^31
+    return fma(dhi, 4294967296.0, dlo);
 }
 
 // 64-bit two's-complement add into (lo[idx], hi[idx]) with two native 32-bit
@@ -465,8 +481,9 @@ k_lwa_fx_prep(long s0, int ny, const double* __restrict__ Qref, int increase,
             sorted[s] = 0; if (any_unsorted) *any_unsorted = 1;
         }
         int hb = 1; while ((1 << hb) < ny + 1) ++hb;                 // sums of up to ny terms
-        const int kS = (MS > 0.0 && isfinite(MS) && !empty) ? 61 - hb - ilogb(MS) : 0;
-        const int kV = (MV > 0.0 && isfinite(MV) && !empty) ? 61 - hb - ilogb(MV) : 0;
+        const int kb = min(51, 62 - hb) - 1;                         // |X| < 2^(kb+1): fx_rn range and 63-bit column sums
+        const int kS = (MS > 0.0 && isfinite(MS) && !empty) ? kb - ilogb(MS) : 0;
+        const int kV = (MV > 0.0 && isfinite(MV) && !empty) ? kb - ilogb(MV) : 0;
         if (empty || !isfinite(f.c)) f.c = 0.0;
         f.sS = scalbn(1.0, kS); f.iS = scalbn(1.0, -kS);
         f.sV = scalbn(1.0, kV); f.iV = scalbn(1.0, -kV);
@@ -475,17 +492,24 @@ k_lwa_fx_prep(long s0, int ny, const double* __restrict__ Qref, int increase,
     }
 }
 
-// the deposit of one cell; used by the scatter phase and re-derived (bit for bit)
-// by the prefix phase
-__device__ __forceinline__ bool fx_terms(double v, double w, double c, double sS, double sV, long long& XS, long long& XV)
+// the deposit of one cell; used by the scatter phase (with negated scales: rn() is
+// odd, so rn(-x) = -rn(x) bit for bit) and re-derived by the prefix phase
+__device__ __forceinline__ void fx_terms(double v, double w, double c, double sS, double sV, long long& XS, long long& XV)
 {
-    const bool valid = (v == v) && (w == w);
-    XS = valid ? __double2ll_rn(__dmul_rn(w, sS)) : 0ll;
-    XV = valid ? __double2ll_rn(__dmul_rn(__dmul_rn(w, __dsub_rn(v, c)), sV)) : 0ll;
-    return valid;
+    XS = fx_rn(__dmul_rn(w, sS));
+    XV = fx_rn(__dmul_rn(__dmul_rn(w, __dsub_rn(v, c)), sV));
 }
+// sign-adjusted value of a cell in fp32 (exact) / fp64 and its fp32 image for the LUT
+__device__ __forceinline__ void fx_value(float qraw, float sgf, double, double& v, float& vf) { vf = sgf * qraw; v = (double)vf; }
+__device__ __forceinline__ void fx_value(double qraw, float, double sg, double& v, float& vf) { v = sg * qraw; vf = (float)v; }
 
-constexpr int FX_U = 4;              // rows whose loads are in flight together
+#ifndef XC_FX_U
+#define XC_FX_U 4
+#endif
+#ifndef XC_FX_PROBES
+#define XC_FX_PROBES 2
+#endif
+constexpr int FX_U = XC_FX_U;        // rows whose loads are in flight together
 
 template <typename QT>
 __global__ void __launch_bounds__(FX_NT, 2)
@@ -493,7 +517,7 @@ k_lwa_fx(const QT* __restrict__ q, long s0, long sbase, int ny, int nx,
          const double* __restrict__ Qref, const double* __restrict__ ww,
          int increase, int part, const int32_t* __restrict__ sorted,
          const FxScale* __restrict__ fxs, const uint32_t* __restrict__ lutg,
-         int Lseg, double* __restrict__ out)
+         double* __restrict__ out)
 {
     const long s = s0 + blockIdx.y;
     if (!sorted[s]) return;
@@ -503,10 +527,11 @@ k_lwa_fx(const QT* __restrict__ q, long s0, long sbase, int ny, int nx,
     uint32_t*  far = reinterpret_cast<uint32_t*>(smem + L.off_far);
     uint32_t*  lut = reinterpret_cast<uint32_t*>(smem + L.off_lut);
     long long* tot = reinterpret_cast<long long*>(smem + L.off_tot);     // [2][FX_TC][FX_TOTP]
-    uint32_t *Slo = far, *Shi = far + L.plane, *Vlo = far + 2 * L.plane, *Vhi = far + 3 * L.plane;
+    const int plane = L.plane;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double sg = increase ? 1.0 : -1.0;
+    const float sgf = increase ? 1.0f : -1.0f;
     const double* Qg = Qref + s * (long)ny;
     const uint32_t* lg = lutg + (size_t)(s - sbase) * FX_LUT;
     for (int j = tid; j < ny; j += FX_NT) Qs[j] = sg * Qg[j];
@@ -514,7 +539,7 @@ k_lwa_fx(const QT* __restrict__ q, long s0, long sbase, int ny, int nx,
     for (int k = 0; k < FX_LUT / FX_NT; ++k) lut[tid + k * FX_NT] = __ldg(lg + tid + k * FX_NT);
     {
         uint4* z = reinterpret_cast<uint4*>(far);
-        for (int k = tid; k < L.plane; k += FX_NT) z[k] = make_uint4(0u, 0u, 0u, 0u);   // 4 planes of L.plane words
+        for (int k = tid; k < plane; k += FX_NT) z[k] = make_uint4(0u, 0u, 0u, 0u);   // 4 planes of `plane` words
     }
     const FxScale* fp = fxs + (s - sbase);
     const double fc = __ldg(&fp->c), fsS = __ldg(&fp->sS), fsV = __ldg(&fp->sV);
@@ -527,48 +552,56 @@ k_lwa_fx(const QT* __restrict__ q, long s0, long sbase, int ny, int nx,
     const bool use_t1 = (part == XC_PART_ALL) || !keep_pos;   // mask -1 region
     const bool use_t2 = (part == XC_PART_ALL) || keep_pos;    // mask +1 region
 
+    // thread = (column c, row segment seg); the segments split the rows evenly
     const int c = tid & (FX_TC - 1), seg = tid / FX_TC;
     const int i = blockIdx.x * FX_TC + c;
     const bool col_ok = i < nx;
-    const int r0 = min(ny, seg * Lseg), r1 = min(ny, r0 + Lseg);
-    const QT* qc = q + s * (long)ny * nx + i;
-    const double* wc = ww + i;
+    const int r0 = (int)(((long)seg * ny) / FX_SEG), r1 = (int)(((long)(seg + 1) * ny) / FX_SEG);
+    const QT* qc = q + (s * (long)ny + r0) * nx + i;
+    const double* wc = ww + (long)r0 * nx + i;
+    uint32_t* fcol = far + c;                                  // word (slot t, plane k) = fcol[t * FX_TC + k * plane]
 
     // ---- scatter: one deposit of -X at the far end of each cell's range ----
     long long ownS = 0, ownV = 0;
     if (col_ok) {
+        const double nsS = -fsS, nsV = -fsV;
+        const QT* qp = qc; const double* wp = wc;
         for (int jb = r0; jb < r1; jb += FX_U) {
             QT qv[FX_U]; double wv[FX_U];
 #pragma unroll
             for (int u = 0; u < FX_U; ++u) {
-                const int jp = min(jb + u, r1 - 1);
-                qv[u] = __ldg(qc + (long)jp * nx); wv[u] = __ldg(wc + (long)jp * nx);
+                const bool ok = jb + u < r1;
+                qv[u] = ok ? __ldg(qp + (long)u * nx) : (QT)CUDART_NAN;
+                wv[u] = ok ? __ldg(wp + (long)u * nx) : 0.0;
             }
+            qp += (long)FX_U * nx; wp += (long)FX_U * nx;
 #pragma unroll
             for (int u = 0; u < FX_U; ++u) {
                 const int jp = jb + u;
-                if (jp >= r1) break;
-                const double v = sg * (double)qv[u];
-                long long XS, XV;
-                if (!fx_terms(v, wv[u], fc, fsS, fsV, XS, XV)) continue;
-                const uint32_t pk = lut[fx_bucket((float)v, qminf, scalef)];
+                double v; float vf;
+                fx_value(qv[u], sgf, sg, v, vf);
+                const double w = wv[u];
+                if (v != v || w != w) continue;                  // NaN cell / NaN weight / past the segment
+                long long NS, NV;                                // -X_S, -X_V
+                fx_terms(v, w, fc, nsS, nsV, NS, NV);
+                const uint32_t pk = lut[fx_bucket(vf, qminf, scalef)];
                 int x = (int)(pk & 0xffffu), e = (int)(pk >> 16);
-                const int e0 = e;                                    // rows >= e0 have Q > v
+                const int e0 = e;                                // rows >= e0 have Q > v
                 while (x < e) { const int mid = (x + e) >> 1; if (Qs[mid] < v) x = mid + 1; else e = mid; }
-                int target = jp + 1;                                 // inactive: cancels the own deposit
-                if (x > jp + 1) { if (use_t1) target = x; }          // x = #{Q < v}
+                int target = jp + 1;                             // inactive: cancels the own deposit
+                if (x > jp + 1) { if (use_t1) target = x; }      // x = #{Q < v}
                 else {
-                    int h = x;                                       // #{Q <= v}; ties live in v's bucket only
+                    int h = x;                                   // #{Q <= v}; ties live in v's bucket only
                     if (h < e0 && Qs[h] == v) {
                         int y = e0; ++h;
                         while (h < y) { const int mid = (h + y) >> 1; if (Qs[mid] <= v) h = mid + 1; else y = mid; }
                     }
                     if (h <= jp && use_t2) target = h;
                 }
-                ownS += XS; ownV += XV;
-                const int idx = target * FX_TC + c;
-                fx_add64(Slo, Shi, idx, -XS);
-                fx_add64(Vlo, Vhi, idx, -XV);
+                ownS -= NS; ownV -= NV;
+                uint32_t* slot = fcol + target * FX_TC;
+                fx_add64(slot, slot + plane, 0, NS);
+                fx_add64(slot + 2 * plane, slot + 3 * plane, 0, NV);
             }
         }
     }
@@ -577,9 +610,9 @@ k_lwa_fx(const QT* __restrict__ q, long s0, long sbase, int ny, int nx,
     // ---- prefix down the columns: segment totals, block scan, final walk ----
     {
         unsigned long long aSl = 0, aVl = 0; long long aSh = 0, aVh = 0;
-        for (int j = r0; j < r1; ++j) {
-            const int idx = j * FX_TC + c;
-            aSl += Slo[idx]; aSh += (int32_t)Shi[idx]; aVl += Vlo[idx]; aVh += (int32_t)Vhi[idx];
+        const uint32_t* sl = fcol + r0 * FX_TC;
+        for (int j = r0; j < r1; ++j, sl += FX_TC) {
+            aSl += sl[0]; aSh += (int32_t)sl[plane]; aVl += sl[2 * plane]; aVh += (int32_t)sl[3 * plane];
         }
         tot[c * FX_TOTP + seg] = (long long)aSl + (aSh << 32) + ownS;
         tot[(FX_TC + c) * FX_TOTP + seg] = (long long)aVl + (aVh << 32) + ownV;
@@ -598,26 +631,34 @@ k_lwa_fx(const QT* __restrict__ q, long s0, long sbase, int ny, int nx,
     if (col_ok) {
         const double fiS = __ldg(&fp->iS), fiV = __ldg(&fp->iV);
         long long RS = tot[c * FX_TOTP + seg], RV = tot[(FX_TC + c) * FX_TOTP + seg];
-        double* oc = out + s * (long)ny * nx + i;
+        double* op = out + (s * (long)ny + r0) * nx + i;
+        const QT* qp = qc; const double* wp = wc;
+        const uint32_t* sl = fcol + r0 * FX_TC;
+        const double* Qj = Qs + r0;
         for (int jb = r0; jb < r1; jb += FX_U) {
             QT qv[FX_U]; double wv[FX_U];
 #pragma unroll
             for (int u = 0; u < FX_U; ++u) {
-                const int j = min(jb + u, r1 - 1);
-                qv[u] = __ldg(qc + (long)j * nx); wv[u] = __ldg(wc + (long)j * nx);
+                const bool ok = jb + u < r1;
+                qv[u] = ok ? __ldg(qp + (long)u * nx) : (QT)CUDART_NAN;
+                wv[u] = ok ? __ldg(wp + (long)u * nx) : 0.0;
             }
+            qp += (long)FX_U * nx; wp += (long)FX_U * nx;
 #pragma unroll
             for (int u = 0; u < FX_U; ++u) {
-                const int j = jb + u;
-                if (j >= r1) break;
-                const int idx = j * FX_TC + c;
-                RS += (long long)(((unsigned long long)Shi[idx] << 32) | Slo[idx]);
-                RV += (long long)(((unsigned long long)Vhi[idx] << 32) | Vlo[idx]);
-                const double Sj = __dmul_rn((double)RS, fiS), Vj = __dmul_rn((double)RV, fiV);
-                oc[(long)j * nx] = sg * (Vj - (Qs[j] - fc) * Sj);
-                long long XS, XV;
-                fx_terms(sg * (double)qv[u], wv[u], fc, fsS, fsV, XS, XV);
-                RS += XS; RV += XV;
+                if (jb + u >= r1) break;
+                RS += (long long)(((unsigned long long)sl[plane] << 32) | sl[0]);
+                RV += (long long)(((unsigned long long)sl[3 * plane] << 32) | sl[2 * plane]);
+                const double Sj = __dmul_rn(fx_to_double(RS), fiS), Vj = __dmul_rn(fx_to_double(RV), fiV);
+                *op = sg * (Vj - (*Qj - fc) * Sj);
+                op += nx; sl += FX_TC; ++Qj;
+                double v; float vf;
+                fx_value(qv[u], sgf, sg, v, vf);
+                if (v == v && wv[u] == wv[u]) {
+                    long long XS, XV;
+                    fx_terms(v, wv[u], fc, fsS, fsV, XS, XV);
+                    RS += XS; RV += XV;
+                }
             }
         }
     }
@@ -998,7 +1039,6 @@ int xc::lwa_impl(const void* q, int q_dtype, long S, int n_eq, int n_x, const do
         FxScale* fxs = reinterpret_cast<FxScale*>(cur);
         const long ch = S < FX_CHUNK ? S : FX_CHUNK;
         uint32_t* lutg = reinterpret_cast<uint32_t*>(cur + (size_t)ch * sizeof(FxScale));
-        int Lseg = (n_eq + FX_SEG - 1) / FX_SEG; Lseg |= 1;       // odd: conflict-free column walks
         if (q_dtype == XC_F32) XC_CUDA_OK(cudaFuncSetAttribute(k_lwa_fx<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL.total));
         else                   XC_CUDA_OK(cudaFuncSetAttribute(k_lwa_fx<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL.total));
         for (long s0 = 0; s0 < S; s0 += FX_CHUNK) {
@@ -1009,10 +1049,10 @@ int xc::lwa_impl(const void* q, int q_dtype, long S, int n_eq, int n_x, const do
             dim3 grid((unsigned)((n_x + FX_TC - 1) / FX_TC), (unsigned)ns);
             if (q_dtype == XC_F32)
                 k_lwa_fx<float><<<grid, FX_NT, FL.total, st>>>((const float*)q, s0, s0, n_eq, n_x, Qref, ww, increase, part, sorted,
-                                                              fxs, lutg, Lseg, out);
+                                                              fxs, lutg, out);
             else
                 k_lwa_fx<double><<<grid, FX_NT, FL.total, st>>>((const double*)q, s0, s0, n_eq, n_x, Qref, ww, increase, part, sorted,
-                                                               fxs, lutg, Lseg, out);
+                                                               fxs, lutg, out);
             XC_LAUNCH_OK();
         }
     } else if (fast) {
