@@ -374,14 +374,15 @@ k_lwa_fast(const QT* __restrict__ q, long s0, int ny, int nx,
 // grid = (ceil(n_x / 8), slices); block = FX_NT threads = (column c, row segment).
 // Shared memory: four u32 planes [slot][column] (lo/hi words of S and V), Q, a
 // 1024-bucket LUT over Q and the per-segment totals of the block scan.
-constexpr int FX_TC  = 8;
-constexpr int FX_NT  = 512;
-constexpr int FX_SEG = FX_NT / FX_TC;      // row segments per column
+// Two tile shapes: 16 columns x 1024 threads (one CTA per SM; a warp-wide global
+// access then covers 2 rows x 64/128 B instead of 4 rows x 32/64 B, which is what
+// the LSU data pipe is paid in) while the four planes fit 227 KB, else 8 x 512.
+constexpr int FX_SEG = 64;                 // row segments per column (threads = FX_SEG * TC)
 constexpr int FX_LUT = 1024;
 constexpr int FX_TOTP = FX_SEG + 2;        // padded row of the totals table
 
 struct LwaFxSmem { size_t off_Q, off_far, off_lut, off_tot, total; int plane; };
-static __host__ __device__ inline LwaFxSmem lwa_fx_layout(int ny)
+static __host__ __device__ inline LwaFxSmem lwa_fx_layout(int ny, int FX_TC)
 {
     LwaFxSmem L;
     L.plane = ((ny + 1) * FX_TC + 3) & ~3;                       // u32 words per plane
@@ -511,8 +512,8 @@ __device__ __forceinline__ void fx_value(double qraw, float, double sg, double& 
 #endif
 constexpr int FX_U = XC_FX_U;        // rows whose loads are in flight together
 
-template <typename QT>
-__global__ void __launch_bounds__(FX_NT, 2)
+template <typename QT, int FX_TC>
+__global__ void __launch_bounds__(FX_SEG * FX_TC, FX_TC <= 8 ? 2 : 1)
 k_lwa_fx(const QT* __restrict__ q, long s0, long sbase, int ny, int nx,
          const double* __restrict__ Qref, const double* __restrict__ ww,
          int increase, int part, const int32_t* __restrict__ sorted,
@@ -522,7 +523,9 @@ k_lwa_fx(const QT* __restrict__ q, long s0, long sbase, int ny, int nx,
     const long s = s0 + blockIdx.y;
     if (!sorted[s]) return;
     extern __shared__ __align__(16) unsigned char smem[];
-    const LwaFxSmem L = lwa_fx_layout(ny);
+    constexpr int FX_NT = FX_SEG * FX_TC;
+    static_assert(FX_NT / 32 >= 2 * FX_TC && FX_LUT % FX_NT == 0, "one scan warp per (accumulator, column)");
+    const LwaFxSmem L = lwa_fx_layout(ny, FX_TC);
     double*    Qs  = reinterpret_cast<double*>(smem + L.off_Q);
     uint32_t*  far = reinterpret_cast<uint32_t*>(smem + L.off_far);
     uint32_t*  lut = reinterpret_cast<uint32_t*>(smem + L.off_lut);
@@ -961,6 +964,7 @@ extern "C" int xc_lwa_weights(const void* dA, int dA_dtype, long P, double* ww,
 
 constexpr int LWA_RNG_C = 8;        // partial (min, max) CTAs per slice in the stand-alone path
 constexpr int LWA_WMAX_N = 128;     // partial max |ww| CTAs
+template <typename QT, typename... A> static const QT* lwa_qptr(void (*)(const QT*, A...)) { return nullptr; }
 constexpr long FX_CHUNK = 1024;     // slices per fixed-point launch (bounds the per-slice LUT scratch)
 size_t xc::lwa_scratch_doubles(long S, bool have_minmax)
 {
@@ -1010,9 +1014,9 @@ int xc::lwa_impl(const void* q, int q_dtype, long S, int n_eq, int n_x, const do
     const bool match = lwa_use_match();
     const int qbytes = q_dtype == XC_F32 ? 4 : 8;
     const int tc = (n_eq < 65535) ? lwa_pick_tc(n_eq, qbytes, !match) : 0;
-    const LwaFxSmem FL = lwa_fx_layout(n_eq);
-    const bool fx = (variant == 1) && lwa_use_fx() && scratch && n_eq < 65535 && FL.total <= 227 * 1024 &&
-                    FX_LUT % FX_NT == 0;
+    const int fx_tc = lwa_fx_layout(n_eq, 16).total <= 227 * 1024 ? 16 : 8;
+    const LwaFxSmem FL = lwa_fx_layout(n_eq, fx_tc);
+    const bool fx = (variant == 1) && lwa_use_fx() && scratch && n_eq < 65535 && FL.total <= 227 * 1024;
     const bool fast = fx || ((variant == 1) && tc >= 1 && (size_t)tc * (n_eq + 2) * 16 >= (size_t)(LWA_LUT + 1) * 2);
     if (fast && !flags_ready) {
         k_check_sorted<<<(unsigned)S, 256, 0, st>>>(Qref, n_eq, increase, sorted);
@@ -1039,21 +1043,22 @@ int xc::lwa_impl(const void* q, int q_dtype, long S, int n_eq, int n_x, const do
         FxScale* fxs = reinterpret_cast<FxScale*>(cur);
         const long ch = S < FX_CHUNK ? S : FX_CHUNK;
         uint32_t* lutg = reinterpret_cast<uint32_t*>(cur + (size_t)ch * sizeof(FxScale));
-        if (q_dtype == XC_F32) XC_CUDA_OK(cudaFuncSetAttribute(k_lwa_fx<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL.total));
-        else                   XC_CUDA_OK(cudaFuncSetAttribute(k_lwa_fx<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL.total));
+        auto launch = [&](auto kern, int tcv, long s0, long ns) -> int {
+            XC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL.total));
+            dim3 grid((unsigned)((n_x + tcv - 1) / tcv), (unsigned)ns);
+            kern<<<grid, FX_SEG * tcv, FL.total, st>>>((decltype(lwa_qptr(kern)))q, s0, s0, n_eq, n_x, Qref, ww, increase, part, sorted, fxs, lutg, out);
+            XC_LAUNCH_OK();
+            return 0;
+        };
         for (long s0 = 0; s0 < S; s0 += FX_CHUNK) {
             const long ns = S - s0 < FX_CHUNK ? S - s0 : FX_CHUNK;
             k_lwa_fx_prep<<<(unsigned)ns, FX_PREP_NT, 0, st>>>(s0, n_eq, Qref, increase, sorted, any_unsorted,
                                                                rng, rngC, wpart, LWA_WMAX_N, fxs, lutg);
             XC_LAUNCH_OK();
-            dim3 grid((unsigned)((n_x + FX_TC - 1) / FX_TC), (unsigned)ns);
-            if (q_dtype == XC_F32)
-                k_lwa_fx<float><<<grid, FX_NT, FL.total, st>>>((const float*)q, s0, s0, n_eq, n_x, Qref, ww, increase, part, sorted,
-                                                              fxs, lutg, out);
-            else
-                k_lwa_fx<double><<<grid, FX_NT, FL.total, st>>>((const double*)q, s0, s0, n_eq, n_x, Qref, ww, increase, part, sorted,
-                                                               fxs, lutg, out);
-            XC_LAUNCH_OK();
+            int rc;
+            if (q_dtype == XC_F32) rc = fx_tc == 16 ? launch(k_lwa_fx<float, 16>, 16, s0, ns) : launch(k_lwa_fx<float, 8>, 8, s0, ns);
+            else                   rc = fx_tc == 16 ? launch(k_lwa_fx<double, 16>, 16, s0, ns) : launch(k_lwa_fx<double, 8>, 8, s0, ns);
+            if (rc) return rc;
         }
     } else if (fast) {
         int rc;
