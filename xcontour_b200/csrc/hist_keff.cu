@@ -110,21 +110,123 @@ __device__ __forceinline__ void hk_tag(double2* H, uint8_t* tag, int bin, double
     }
 }
 
+#ifndef XC_HKX_MATCH     /* 0: always direct adds; 1: register pre-combination in crowded warp steps; 2: in every step */
+#define XC_HKX_MATCH 1
+#endif
+#ifndef XC_HKX_CROWD     /* neighbouring-lane bin matches (of 31) that make a warp step `crowded` */
+#define XC_HKX_CROWD 8
+#endif
+
+// ---------------------------------------------------------------------------
+// Exact accumulation on native shared-memory integer atomics (default).
+// Measured on B200 (scripts/micro/atoms_bench.cu): ATOMS.ADD.U32 costs ~3 cycles per
+// warp instruction even with bank conflicts and colliding addresses, one
+// conflict-free fp64-pair read-modify-write round 15-18 (and the lanes of a warp that
+// share a bin need one round each).  A term x = m * 2^(ex-1075) (m: 53-bit mantissa)
+// is added as the integer m << sh into a 96-bit accumulator of the window
+// w = (ex - e_base) / 24, sh = (ex - e_base) % 24: inside a window every add is exact
+// and order-independent, HKX_NW windows cover 144 binary orders of magnitude (the
+// polar rows of a lat-lon grid put |grad q|^2 dA 2^108 above the mid-latitude
+// values), and a CTA's <= 2^18 terms per bin cannot overflow 96 bits (77 + 18).
+// e_base comes from the smallest term of the CTA's first 2048 cells; terms below it
+// are truncated at 2^-52 of the base scale, terms above the top window, negative or
+// non-finite ones take an fp64 CAS add into a side table (never on sane data).  All
+// warps of a CTA share ONE set of accumulators, so there is no lane election at all;
+// only in warp steps where neighbouring lanes sit in the same bin (smooth stretches,
+// where the atomic unit would serialise the colliding lanes) the lanes of a bin are
+// first combined in registers as in hk_scatter.
+constexpr int HKX_NW = 6;
+constexpr int HKX_WBITS = 24;
+constexpr int HKX_MARGIN = 12;           // windows start this many bits below the smallest sampled term
+
+__device__ __forceinline__ void hkx_add(uint32_t* acc, double* esc, int N, int bin, int e_base, double x)
+{
+    const int hi = __double2hiint(x);
+    const uint32_t lo = (uint32_t)__double2loint(x);
+    const int ex = (hi >> 20) & 0x7ff;
+    int rel = ex - e_base;
+    if (hi < 0 || ex == 0x7ff || ex == 0 || rel >= HKX_NW * HKX_WBITS) {
+        if (x != 0.0) atomicAdd(esc + bin, x);               // negative, non-finite, denormal, above the top window
+        return;
+    }
+    unsigned long long m = ((unsigned long long)(uint32_t)((hi & 0xfffff) | 0x100000) << 32) | lo;
+    if (rel < 0) { m = rel > -53 ? (m >> (-rel)) : 0ull; rel = 0; }
+    const int w = (rel * 2731) >> 16;                        // rel / 24 for rel < 8192
+    const int sh = rel - w * HKX_WBITS;
+    const unsigned long long v = m << sh;
+    const uint32_t v0 = (uint32_t)v, v1 = (uint32_t)(v >> 32);
+    const uint32_t v2 = sh > 11 ? (uint32_t)(m >> (64 - sh)) : 0u;
+    uint32_t* s = acc + ((size_t)w * N + bin) * 3;
+    const uint32_t o0 = atomicAdd(s, v0);
+    const uint32_t c0 = (uint32_t)((o0 + v0) < v0);
+    const uint32_t t1 = v1 + c0;
+    const uint32_t o1 = atomicAdd(s + 1, t1);
+    const uint32_t c1 = (uint32_t)(t1 < c0) + (uint32_t)((o1 + t1) < t1);
+    atomicAdd(s + 2, v2 + c1);
+}
+// exponent field of a term that can anchor the windows (positive, finite, normal), else INT_MAX
+__device__ __forceinline__ int hkx_exp(double x)
+{
+    const int hi = __double2hiint(x);
+    const int ex = (hi >> 20) & 0x7ff;
+    return (hi > 0 && ex != 0x7ff && ex != 0) ? ex : 0x7fffffff;
+}
+// value of a window's 96-bit accumulator times 2^(unit exponent)
+__device__ __forceinline__ double hkx_window(const uint32_t* s, int unit_exp)
+{
+    const double d = fma((double)s[2], 18446744073709551616.0, fma((double)s[1], 4294967296.0, (double)s[0]));
+    return ldexp(d, unit_exp);
+}
+// one scatter step of the fixed-point path: lanes that share a bin with more than 3
+// others are combined in registers first (pointer jumping over the MATCH.ANY peer
+// list, fixed lane order), everybody else adds directly
+__device__ __forceinline__ void hkx_scatter(uint32_t* accA, uint32_t* accG, double* escA, double* escG, int N,
+                                            int eA, int eG, int bin, double w0, double w1, int lane, bool crowded)
+{
+#if XC_HKX_MATCH
+    if (XC_HKX_MATCH == 2 || crowded) {                          // warp-uniform
+        const bool a = bin >= 0;
+        const unsigned pr = hk_match(bin, lane);
+        const unsigned above = (lane == 31) ? 0u : (pr & (0xffffffffu << (lane + 1)));
+        int nxt = above ? (__ffs(above) - 1) : -1;
+        const bool leader = a && ((__ffs(pr) - 1) == lane);
+        while (__any_sync(XC_FULL, nxt >= 0)) {
+            const int src = nxt >= 0 ? nxt : lane;
+            const double g0 = __shfl_sync(XC_FULL, w0, src), g1 = __shfl_sync(XC_FULL, w1, src);
+            const int gn = __shfl_sync(XC_FULL, nxt, src);
+            if (nxt >= 0) { w0 += g0; w1 += g1; nxt = gn; }
+        }
+        if (leader) { hkx_add(accA, escA, N, bin, eA, w0); hkx_add(accG, escG, N, bin, eG, w1); }
+        return;
+    }
+#endif
+    if (bin >= 0) { hkx_add(accA, escA, N, bin, eA, w0); hkx_add(accG, escG, N, bin, eG, w1); }
+}
+
 // grid = (C, nslices), block = 16 warps, 2 CTAs per SM.
+template <bool FX>
 __global__ void __launch_bounds__(HK_WARPS * 32, 2)
 k_hist_keff(const HistKeffParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int N = p.N;
     double*  e = reinterpret_cast<double*>(smem);
-    double2* H = reinterpret_cast<double2*>(e + ((N + 2) & ~1));      // [warp][N]
+    double2* H = reinterpret_cast<double2*>(e + ((N + 2) & ~1));      // !FX: [warp][N]
+    double*   esc = reinterpret_cast<double*>(H);                     //  FX: [2][N] side table, then
+    uint32_t* acc = reinterpret_cast<uint32_t*>(esc + 2 * N);         //      [2][HKX_NW][N][3] window accumulators
+    const size_t accn = (size_t)HKX_NW * N * 3;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long s = p.s0 + blockIdx.y;
     const int c = blockIdx.x, C = gridDim.x;
 
     const double* eg = p.edges + s * (long)(N + 1);
     for (int k = tid; k <= N; k += blockDim.x) e[k] = eg[k];
-    for (int i = tid; i < HK_WARPS * N; i += blockDim.x) H[i] = make_double2(0.0, 0.0);
+    if (FX) {
+        for (int i = tid; i < 2 * N; i += blockDim.x) esc[i] = 0.0;
+        for (int i = tid; i < (int)(2 * accn); i += blockDim.x) acc[i] = 0u;
+    } else {
+        for (int i = tid; i < HK_WARPS * N; i += blockDim.x) H[i] = make_double2(0.0, 0.0);
+    }
     __syncthreads();
     const double span = e[N] - e[0];
     const float basef = (float)e[0];
@@ -153,7 +255,12 @@ k_hist_keff(const HistKeffParams p)
     uint8_t* tagw = reinterpret_cast<uint8_t*>(H + (size_t)HK_WARPS * N) + (size_t)warp * ((N + 15) & ~15);
     (void)tagw;
 
-    for (int base = beg + warp * 128; base < end; base += HK_WARPS * 128) {
+    __shared__ int sbase[2 * HK_WARPS];
+    bool first = true; int eA = 0, eG = 0;
+    // (FX) every warp of the CTA takes part in the first step -- `per` is a multiple of HK_WARPS*128 or the
+    // loop bound below is padded so that the anchoring barrier is reached by all threads
+    const int end_it = FX ? beg + ((end - beg + HK_WARPS * 128 - 1) / (HK_WARPS * 128)) * (HK_WARPS * 128) : end;
+    for (int base = beg + warp * 128; base < end_it; base += HK_WARPS * 128) {
         const int i0 = base + lane * 4;
         const bool ok = i0 < end;                       // P, per and nx are multiples of 4: all-or-nothing
         int j = 0, col = 0;
@@ -187,6 +294,41 @@ k_hist_keff(const HistKeffParams p)
         double p2 = __dmul_rn(g2, (double)a4.z), p3 = __dmul_rn(g3, (double)a4.w);
         p0 = (p0 == p0) ? p0 : 0.0; p1 = (p1 == p1) ? p1 : 0.0;
         p2 = (p2 == p2) ? p2 : 0.0; p3 = (p3 == p3) ? p3 : 0.0;
+        if (FX) {
+            if (first) {                                    // anchor the windows on the CTA's first cells
+                first = false;
+                int mA = min(min(hkx_exp(b0 >= 0 ? a0 : 0.0), hkx_exp(b1 >= 0 ? a1 : 0.0)), min(hkx_exp(b2 >= 0 ? a2 : 0.0), hkx_exp(b3 >= 0 ? a3 : 0.0)));
+                int mG = min(min(hkx_exp(b0 >= 0 ? p0 : 0.0), hkx_exp(b1 >= 0 ? p1 : 0.0)), min(hkx_exp(b2 >= 0 ? p2 : 0.0), hkx_exp(b3 >= 0 ? p3 : 0.0)));
+                mA = __reduce_min_sync(XC_FULL, mA); mG = __reduce_min_sync(XC_FULL, mG);
+                if (lane == 0) { sbase[warp] = mA; sbase[HK_WARPS + warp] = mG; }
+                __syncthreads();
+                mA = 0x7fffffff; mG = 0x7fffffff;
+                for (int w = 0; w < HK_WARPS; ++w) { mA = min(mA, sbase[w]); mG = min(mG, sbase[HK_WARPS + w]); }
+                eA = (mA == 0x7fffffff ? 1023 - 72 : mA) - HKX_MARGIN;
+                eG = (mG == 0x7fffffff ? 1023 - 72 : mG) - HKX_MARGIN;
+            }
+            // smooth stretch of the field (neighbouring lanes in the same bin): combine in registers first
+            const int nb = __shfl_down_sync(XC_FULL, b0, 1);
+            const bool crowded = __popc(__ballot_sync(XC_FULL, b0 >= 0 && b0 == nb)) >= XC_HKX_CROWD;
+            if (crowded) {                                  // the lane's own four cells first
+                int c1 = b1, c2 = b2, c3 = b3;
+                double x0 = a0, y0 = p0, x1 = a1, y1 = p1, x2 = a2, y2 = p2, x3 = a3, y3 = p3;
+                if (c1 >= 0 && c1 == b0) { x0 += x1; y0 += y1; c1 = -1; }
+                if (c2 >= 0) { if (c2 == b0) { x0 += x2; y0 += y2; c2 = -1; } else if (c2 == c1) { x1 += x2; y1 += y2; c2 = -1; } }
+                if (c3 >= 0) { if (c3 == b0) { x0 += x3; y0 += y3; c3 = -1; } else if (c3 == c1) { x1 += x3; y1 += y3; c3 = -1; }
+                               else if (c3 == c2) { x2 += x3; y2 += y3; c3 = -1; } }
+                hkx_scatter(acc, acc + accn, esc, esc + N, N, eA, eG, b0, x0, y0, lane, true);
+                if (__any_sync(XC_FULL, c1 >= 0)) hkx_scatter(acc, acc + accn, esc, esc + N, N, eA, eG, c1, x1, y1, lane, true);
+                if (__any_sync(XC_FULL, c2 >= 0)) hkx_scatter(acc, acc + accn, esc, esc + N, N, eA, eG, c2, x2, y2, lane, true);
+                if (__any_sync(XC_FULL, c3 >= 0)) hkx_scatter(acc, acc + accn, esc, esc + N, N, eA, eG, c3, x3, y3, lane, true);
+            } else {
+                hkx_scatter(acc, acc + accn, esc, esc + N, N, eA, eG, b0, a0, p0, lane, false);
+                hkx_scatter(acc, acc + accn, esc, esc + N, N, eA, eG, b1, a1, p1, lane, false);
+                hkx_scatter(acc, acc + accn, esc, esc + N, N, eA, eG, b2, a2, p2, lane, false);
+                hkx_scatter(acc, acc + accn, esc, esc + N, N, eA, eG, b3, a3, p3, lane, false);
+            }
+            continue;
+        }
 #if XC_HK_DEDUP == 0
         hk_scatter(Hw, b0, a0, p0, lane);
         hk_scatter(Hw, b1, a1, p1, lane);
@@ -212,6 +354,19 @@ k_hist_keff(const HistKeffParams p)
     }
     __syncthreads();
     double* out = p.part + ((size_t)(blockIdx.y + p.s0) * C + c) * 2 * N;
+    if (FX) {
+        for (int idx = tid; idx < 2 * N; idx += blockDim.x) {
+            const int k = idx / N, n = idx - k * N;
+            const int eb = k == 0 ? eA : eG;
+            const uint32_t* a = acc + (size_t)k * accn + (size_t)n * 3;
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < HKX_NW; ++w)                     // smallest window first
+                t += hkx_window(a + (size_t)w * N * 3, eb + w * HKX_WBITS - 1075);
+            out[idx] = t + esc[idx];
+        }
+        return;
+    }
     for (int idx = tid; idx < 2 * N; idx += blockDim.x) {
         const int k = idx / N, n = idx - k * N;
         double acc = 0.0;
@@ -237,21 +392,29 @@ int xc::hist_keff_try(const void* q, int q_dtype, long S, long P, const double* 
     if (q_dtype != XC_F32 || dA_dtype != XC_F32 || !st) return 1;
     if ((P & 3) || (st->nx & 3) || P >= (1L << 30) || st->nx < 8) return 1;
     if ((((uintptr_t)q) & 15) || (((uintptr_t)dA) & 15)) return 1;
-    const size_t smem = (size_t)((N + 2) & ~1) * 8 + (size_t)HK_WARPS * N * 16 + (size_t)HK_WARPS * ((N + 15) & ~15);
-    if (smem > 100 * 1024) return 1;                  // two CTAs per SM
     static const char* off = getenv("XCB200_NO_HIST_KEFF");
     if (off) return 1;
+    // XCB200_HIST_FX=0: warp-private fp64 histograms with lane de-duplication instead of the
+    // exact integer accumulators (A/B timing, cross-check in the tests)
+    static const char* fxe = getenv("XCB200_HIST_FX");
+    const size_t smem_fx = (size_t)((N + 2) & ~1) * 8 + (size_t)2 * N * 8 + (size_t)2 * HKX_NW * N * 3 * 4;
+    const size_t smem_rmw = (size_t)((N + 2) & ~1) * 8 + (size_t)HK_WARPS * N * 16 + (size_t)HK_WARPS * ((N + 15) & ~15);
+    const long per = (((P + C - 1) / C) + 3) & ~3L;
+    const bool fx = !(fxe && fxe[0] == '0') && smem_fx <= 113 * 1024 && per <= (1L << 18);   // <= 2^18 terms of < 2^77 per bin and CTA: 95 bits
+    const size_t smem = fx ? smem_fx : smem_rmw;
+    if (smem > 100 * 1024 && !fx) return 1;           // two CTAs per SM
     HistKeffParams p;
-    p.q = (const float*)q; p.P = (int)P; p.per = (int)((((P + C - 1) / C) + 3) & ~3L);
+    p.q = (const float*)q; p.P = (int)P; p.per = (int)per;
     p.edges = edges; p.N = N; p.dA = (const float*)dA;
     p.ny = st->ny; p.nx = st->nx; p.cx = st->cx; p.cy = st->cy; p.part = part;
-    if (cudaFuncSetAttribute(k_hist_keff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(fx ? k_hist_keff<true> : k_hist_keff<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         set_error("k_hist_keff: cannot reserve %zu bytes of shared memory", smem); return 2;
     }
     for (long s0 = 0; s0 < S; s0 += 65535) {
         const long ns = S - s0 < 65535 ? S - s0 : 65535;
         p.s0 = s0;
-        k_hist_keff<<<dim3((unsigned)C, (unsigned)ns), HK_WARPS * 32, smem, (cudaStream_t)stream>>>(p);
+        if (fx) k_hist_keff<true><<<dim3((unsigned)C, (unsigned)ns), HK_WARPS * 32, smem, (cudaStream_t)stream>>>(p);
+        else    k_hist_keff<false><<<dim3((unsigned)C, (unsigned)ns), HK_WARPS * 32, smem, (cudaStream_t)stream>>>(p);
         count_launch();
         if (cudaGetLastError() != cudaSuccess) { set_error("k_hist_keff launch failed"); return 2; }
     }
