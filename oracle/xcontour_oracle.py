@@ -395,7 +395,7 @@ def cal_local_wave_activity(q, Q, dA, coord, increase, part="all",
     dA = np.asarray(dA)
     coord = np.asarray(coord)
     S, ny, nx = q.shape
-    wei = dA / dA.max()                                  # core.py:723-724
+    wei = dA / np.nanmax(dA)                             # core.py:723-724 (xarray .max() skips NaN)
     coord_incre = not (coord[-1] < coord[0])             # core.py:736-738
     if mask_idx is not None and max(mask_idx) >= ny:
         raise Exception("indices in mask_idx out of boundary")
@@ -435,7 +435,7 @@ def cal_local_wave_activity_fast(q, Q, dA, coord, increase, part="all"):
     # note: the reference's ``m`` (core.py:757) is "j' >= j" in INDEX space for
     # either direction of a strictly monotone coordinate, so ``coord`` drops out.
     # wei = dA/dA.max() is rounded in dA's own dtype (core.py:723-724)
-    ww = (dA / dA.max()).astype(np.float64) * dA.astype(np.float64)
+    ww = (dA / np.nanmax(dA)).astype(np.float64) * dA.astype(np.float64)
     sgn = 1.0 if increase else -1.0
     keep_pos = (part == "upper") == bool(increase)
     out = np.zeros((S, ny, nx))

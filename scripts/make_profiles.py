@@ -28,7 +28,7 @@ def val(r, k):
 tr = {}
 for r in rr[2:]:
     n = r[idx['Kernel Name']]
-    key = 'lwa' if 'k_lwa_fast' in n else 'bin_accumulate' if 'k_hist' in n else 'minmax_levels' if 'minmax' in n else 'epilogue' if 'epilogue' in n else None
+    key = 'lwa' if ('k_lwa_fx<' in n or 'k_lwa_fast' in n) else 'bin_accumulate' if 'k_hist' in n else 'minmax_levels' if 'minmax' in n else 'epilogue' if 'epilogue' in n else None
     if key and key not in tr:
         grid = r[idx['launch__grid_size']]
         tr[key] = {'dram_bytes_read': val(r, 'dram__bytes_read.sum'), 'dram_bytes_write': val(r, 'dram__bytes_write.sum'),

@@ -272,6 +272,92 @@ def test_lwa_unsorted_profile_nan_and_fp64(ops, vort):
     assert relmax(out, ref) <= RTOL_FIELD * 1e-2 and np.all(out[0, 3] == 0)
 
 
+@pytest.mark.parametrize("increase", [True, False])
+def test_lwa_fixed_point_ties_and_homogenised_patches(ops, increase):
+    """Fixed-point LWA kernel on the inputs that stress its exact parts: a tracer
+    quantised to few distinct values (dozens of cells of a column share one slot of
+    the difference array), tracer values that hit profile values exactly, flat
+    stretches in the profile, NaN cells and NaN weights -- against the reference
+    j-loop.  Integer accumulation is order-independent: two runs are bit-identical."""
+    rng = np.random.default_rng(5)
+    ny, nx = 97, 53                                                  # ragged: 53 = 3 tiles of 16 + 5
+    y = np.linspace(-1, 1, ny)[:, None]
+    q = y + 0.4 * np.sin(np.linspace(0, 12.56, nx))[None, :] * (1 - y ** 2) + 0.03 * rng.standard_normal((ny, nx))
+    q = (np.round(q * 16) / 16).astype(np.float32)                   # homogenised patches
+    q3 = np.stack([q, q[::-1], -q])
+    dA = (0.5 + rng.random((ny, nx))).astype(np.float64)
+    dA[11, 7] = np.nan                                               # NaN weight: that cell contributes nothing
+    Q = np.sort(rng.choice(np.unique(q3), size=(3, ny)).astype(np.float64), axis=1)   # exact hits + flat stretches
+    if not increase:
+        Q = Q[:, ::-1].copy()
+    q3[1, 40:44, 10:20] = np.nan
+    coord = np.arange(ny, dtype=np.float64)
+    for part in ("all", "upper", "lower"):
+        ref = O.cal_local_wave_activity(q3, Q, dA, coord, increase, part)
+        ww = ops.lwa_weights(dev(ops, dA.reshape(-1)))
+        out = ops.lwa(dev(ops, q3), dev(ops, Q), ww, increase, part, 1)
+        assert relmax(out.cpu().numpy(), ref) <= RTOL_FIELD * 1e-2
+        out2 = ops.lwa(dev(ops, q3), dev(ops, Q), ww, increase, part, 1)
+        assert torch.equal(out, out2)
+
+
+def test_lwa_fixed_point_hands_infinities_to_the_exact_loop(ops, vort):
+    """A slice with an infinite tracer value cannot be scaled to fixed point: the
+    preparation kernel flags it and the exact O(n^2) kernel computes it, the other
+    slices stay on the fast path."""
+    lat, lon, q = vort
+    dA = O.latlon_cell_area(lat, lon)[::4, ::8].copy()
+    q3 = np.stack([q[::4, ::8], q[::4, ::8][::-1], q[::4, ::8]]).astype(np.float32)
+    lat4 = lat[::4]
+    Q = _sorted_profile(q3, lat4, dA, 41, True)
+    q3[1, 20, 5] = np.inf
+    with np.errstate(invalid="ignore"):
+        ref = O.cal_local_wave_activity(q3, Q, dA, lat4, True)
+    ww = ops.lwa_weights(dev(ops, dA.reshape(-1)))
+    out = ops.lwa(dev(ops, q3), dev(ops, Q), ww, True, "all", 1).cpu().numpy()
+    for s in (0, 2):
+        assert relmax(out[s], ref[s]) <= RTOL_FIELD * 1e-2
+    fin = np.isfinite(ref[1])
+    assert np.array_equal(np.isfinite(out[1]), fin)
+    assert relmax(out[1][fin], ref[1][fin]) <= RTOL_FIELD * 1e-2
+    assert np.array_equal(np.isinf(out[1]), np.isinf(ref[1])) and np.array_equal(np.isnan(out[1]), np.isnan(ref[1]))
+
+
+def test_fixed_point_and_fp64_accumulators_agree(ops):
+    """Cross-check inside the product: the exact integer accumulators (default) and
+    the fp64 read-modify-write kernels (XCB200_LWA_FX=0, XCB200_HIST_FX=0) are two
+    implementations of the same sums; a fresh process with the switches off must
+    reproduce the fused batch within the summation-order tolerance."""
+    import subprocess, sys, tempfile
+    from conftest import ROOT
+    code = (
+        "import sys, numpy as np, torch; sys.path.insert(0, %r)\n"
+        "import bench\n"
+        "from xcontour_b200.pipeline import KeffLwaPlan\n"
+        "from xcontour_b200 import utils\n"
+        "lat, lon = bench.grid()\n"
+        "dA = utils.latlon_cell_area(lat, lon).astype(np.float32)\n"
+        "plan = KeffLwaPlan(lat, lon, dA, bench.NLEV)\n"
+        "q = torch.from_numpy(np.stack([bench.synth_slice_np(k, lat, lon) for k in range(3)])).cuda()\n"
+        "out = plan.run(q)\n"
+        "torch.cuda.synchronize()\n"
+        "np.savez(sys.argv[1], **{k: v.cpu().numpy() for k, v in out.items()})\n" % ROOT)
+    res = []
+    with tempfile.TemporaryDirectory() as td:
+        for i, env in enumerate(({}, {"XCB200_LWA_FX": "0", "XCB200_HIST_FX": "0"})):
+            f = os.path.join(td, "o%d.npz" % i)
+            r = subprocess.run([sys.executable, "-c", code, f], env=dict(os.environ, **env),
+                               capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+            res.append(dict(np.load(f)))
+    a, b = res
+    assert np.array_equal(a["ctr"], b["ctr"])
+    assert relmax(a["area"], b["area"]) <= RTOL_INT and relmax(a["intgrdS"], b["intgrdS"]) <= 1e-11
+    _close(a["dqdA"], b["dqdA"], 1e-10)
+    _close(a["Qref"], b["Qref"], 1e-11)
+    assert relmax(a["lwa"], b["lwa"]) <= RTOL_FIELD * 1e-2
+
+
 def test_lwa_variant2_and_masks(ops, vort):
     lat, lon, q = vort
     dA = O.latlon_cell_area(lat, lon).astype(np.float32)
@@ -755,8 +841,10 @@ def test_contour2d_1d_area_explicit_levels_check_mono(ops, vort):
 
 
 @pytest.mark.parametrize("env", [
-    {"XCB200_LWA_HEAVY": "3"},                                   # register pre-reduction in the LWA scatter
-    {"XCB200_LWA_DEDUP": "m"},                                   # MATCH.ANY peel in the LWA scatter
+    {"XCB200_LWA_FX": "0"},                                      # fp64 read-modify-write LWA kernel (byte-tag election)
+    {"XCB200_LWA_FX": "0", "XCB200_LWA_HEAVY": "3"},             # ... with register pre-reduction in the scatter
+    {"XCB200_LWA_FX": "0", "XCB200_LWA_DEDUP": "m"},             # ... with the MATCH.ANY peel
+    {"XCB200_HIST_FX": "0"},                                     # warp-private fp64 histograms in the fused Keff pass
     {"XCB200_HIST_DEDUP": "t", "XCB200_NO_HIST_KEFF": "1"},      # byte tags in the general binning kernel
     {"XCB200_NO_HIST_KEFF": "1", "XCB200_OVERLAP": "0"},         # general binning kernel, serial schedule
     {"XCB200_SUB_BATCH": "1"},                                   # one slice per pass, two passes in flight
