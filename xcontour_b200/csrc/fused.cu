@@ -80,6 +80,7 @@ FusedPlan fused_plan(long S, int ny, int nx, int N, long sub_req)
     t += align_up((size_t)p.sub * 16, 256) + align_up(lwa_scratch_doubles(p.sub, true) * 8, 256);   // (min, max), LWA scratch
     t *= XC_LANES;                                          // passes in flight (one per internal stream)
     t += 2 * align_up((size_t)ny * 8, 256);                 // row metrics
+    t += align_up(lwa_wmax_doubles() * 8, 256);              // max |ww| partials
     p.total = t + 8192;
     return p;
 }
@@ -131,10 +132,12 @@ extern "C" int xc_keff_lwa_batch(const xc_keff_lwa_args* a, void* workspace, siz
     }
     double* rcos = ar.take<double>((size_t)ny);
     double* dphi = ar.take<double>((size_t)ny);
+    double* wmaxp = ar.take<double>(lwa_wmax_doubles());
     XC_REQUIRE(ar.ok(), "xc_keff_lwa_batch: workspace accounting error");
 
     StencilArgs sa; sa.ny = ny; sa.nx = nx; sa.cx = rcos; sa.cy = dphi;
     if (stencil) { if (row_metrics(a->lat_rad, ny, a->dlambda, rcos, dphi, stream)) return 1; }
+    if (a->lwa) { if (lwa_wmax(a->ww, P, wmaxp, stream)) return 1; }      // once per call, before the passes fork
     cudaStream_t st = (cudaStream_t)stream;
     const long npass = (S + pl.sub - 1) / pl.sub;
     // optional per-stage timing (forces the serial schedule so that stages do not overlap)
@@ -195,7 +198,7 @@ extern "C" int xc_keff_lwa_batch(const xc_keff_lwa_args* a, void* workspace, siz
         // (6) LWA
         if (a->lwa)
             if (lwa_impl(q, a->q_dtype, ns, ny, nx, Qref, a->ww, a->increase, a->part, 1,
-                         a->lwa + (size_t)s0 * P, L.sorted, L.any_unsorted, true, L.minmax, L.lwa_scratch, ps)) return 1;
+                         a->lwa + (size_t)s0 * P, L.sorted, L.any_unsorted, true, L.minmax, L.lwa_scratch, ps, wmaxp)) return 1;
         mark(5);
         ++pass;
     }

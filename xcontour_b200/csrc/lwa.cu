@@ -395,27 +395,17 @@ static __host__ __device__ inline LwaFxSmem lwa_fx_layout(int ny, int FX_TC)
     return L;
 }
 
-// The conversion instructions (F2I / I2F / F2F with a 64-bit side) run on the XU
-// pipe at a fraction of the ALU rate and were what bound the first version of this
-// kernel; the conversions below use the classic magic-number forms on the FMA /
-// fp64 / integer pipes instead (scripts/micro/cvt_bench.cu).
+// (Conversions: F2I / I2F with a 64-bit side cost ~2.3 cycles per warp instruction on
+// the XU pipe, scripts/micro/cvt_bench.cu; the magic-number forms on the fp64 / integer
+// pipes measure the same or worse and cost issue slots, which is what this kernel is
+// short of, so the hardware conversions stay.)
 __device__ __forceinline__ int fx_bucket(float vf, float qminf, float scalef)
 {
     const float t = fminf(fmaxf((vf - qminf) * scalef, 0.0f), (float)(FX_LUT - 1));
-    return __float_as_int(t + 12582912.0f) - 0x4B400000;        // rn(t), 0 <= t <= 1023; monotone like the rz form
+    return __float2int_rz(t);
 }
-// rn(x) for |x| <= 2^51 (round to nearest even, like __double2ll_rn)
-__device__ __forceinline__ long long fx_rn(double x)
-{
-    return __double_as_longlong(__dadd_rn(x, 6755399441055744.0)) - 0x4338000000000000ll;   // 1.5 * 2^52
-}
-// (double)r, correctly rounded, for any 64-bit r
-__device__ __forceinline__ double fx_to_double(long long r)
-{
-    const double dlo = __hiloint2double(0x43300000, (int)(uint32_t)r) - 4503599627370496.0;                    // 2^52
-    const double dhi = __hiloint2double(0x43300000, (int)((uint32_t)(r >> 32) ^ 0x80000000u)) - 4503601774854144.0; // 2^52 + 2^31
-    return fma(dhi, 4294967296.0, dlo);
-}
+__device__ __forceinline__ long long fx_rn(double x) { return __double2ll_rn(x); }
+__device__ __forceinline__ double fx_to_double(long long r) { return (double)r; }
 
 // 64-bit two's-complement add into (lo[idx], hi[idx]) with two native 32-bit
 // shared atomics; the carry out of the low word is decided by the value the low
@@ -1000,9 +990,18 @@ static bool lwa_use_fx()
     return v == 1;
 }
 
+size_t xc::lwa_wmax_doubles() { return LWA_WMAX_N; }
+int xc::lwa_wmax(const double* ww, long P, double* parts, void* stream)
+{
+    k_absmax_partial<<<LWA_WMAX_N, 256, 0, (cudaStream_t)stream>>>(ww, P, parts);
+    XC_LAUNCH_OK();
+    return 0;
+}
+
 int xc::lwa_impl(const void* q, int q_dtype, long S, int n_eq, int n_x, const double* Qref, const double* ww,
                  int increase, int part, int variant, double* out, int32_t* sorted,
-                 int32_t* any_unsorted, bool flags_ready, const double* minmax, double* scratch, void* stream)
+                 int32_t* any_unsorted, bool flags_ready, const double* minmax, double* scratch, void* stream,
+                 const double* wmax_ready)
 {
     XC_REQUIRE(q && Qref && ww && out, "xc_lwa: null pointer");
     XC_REQUIRE(S > 0 && n_eq >= 1 && n_x >= 1, "xc_lwa: need S>0, n_eq>=1, n_x>=1");
@@ -1036,8 +1035,12 @@ int xc::lwa_impl(const void* q, int q_dtype, long S, int n_eq, int n_x, const do
                 XC_LAUNCH_OK();
             }
         }
-        k_absmax_partial<<<LWA_WMAX_N, 256, 0, st>>>(ww, P, wpart);
-        XC_LAUNCH_OK();
+        const double* wparts = wmax_ready;
+        if (!wparts) {
+            k_absmax_partial<<<LWA_WMAX_N, 256, 0, st>>>(ww, P, wpart);
+            XC_LAUNCH_OK();
+            wparts = wpart;
+        }
         char* cur = reinterpret_cast<char*>(scratch + LWA_WMAX_N + 32 + (minmax ? 0 : (size_t)S * LWA_RNG_C * 2));
         cur = reinterpret_cast<char*>(align_up((size_t)cur, 64));
         FxScale* fxs = reinterpret_cast<FxScale*>(cur);
@@ -1053,7 +1056,7 @@ int xc::lwa_impl(const void* q, int q_dtype, long S, int n_eq, int n_x, const do
         for (long s0 = 0; s0 < S; s0 += FX_CHUNK) {
             const long ns = S - s0 < FX_CHUNK ? S - s0 : FX_CHUNK;
             k_lwa_fx_prep<<<(unsigned)ns, FX_PREP_NT, 0, st>>>(s0, n_eq, Qref, increase, sorted, any_unsorted,
-                                                               rng, rngC, wpart, LWA_WMAX_N, fxs, lutg);
+                                                               rng, rngC, wparts, LWA_WMAX_N, fxs, lutg);
             XC_LAUNCH_OK();
             int rc;
             if (q_dtype == XC_F32) rc = fx_tc == 16 ? launch(k_lwa_fx<float, 16>, 16, s0, ns) : launch(k_lwa_fx<float, 8>, 8, s0, ns);
