@@ -331,7 +331,9 @@ def run_ours(args, rank, world, local_rank):
                        "parallelism": "slices sharded over %d GPU(s), no data-path collective" % world},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": traffic,
-                         "traffic_note": "ncu dram bytes per launch of 16 slices (profiles/traffic.json)",
+                         "traffic_note": "ncu dram__bytes_read+write of one launch = one pass of 32 slices "
+                                         "(profiles/traffic.json); algorithmic bytes of the same launch in alg_bytes_per_launch",
+                         "alg_bytes_per_launch": STAGE_ALG_BYTES[dom] * 32,
                          "peak_source": peak_src,
                          "stage_ms_per_step": stages,
                          "pipeline": {"alg_bytes_per_slice": ALG_BYTES_PER_SLICE,
