@@ -1,0 +1,62 @@
+"""
+oracle/refshim -- run the reference's own, unmodified ``xcontour/core.py`` in an image
+that has neither xarray nor xhistogram (TEST INFRASTRUCTURE; never imported by the
+product).
+
+    from oracle import refshim
+    ref = refshim.load_reference("/root/reference")     # the `xcontour` package
+    ref.Contour2D(...)
+
+``load_reference`` registers stand-in modules for the third-party imports of
+``xcontour/core.py:8-13`` and ``xcontour/utils.py:8-12`` (xarray, xhistogram.xarray,
+skimage.measure, xgcm, xgcm.autogenerate -- the last three are only touched by code
+outside the hot path and are empty stubs) and imports the package from the given
+directory without copying it.  /root/reference does not exist on the GPU box: only
+the fixture generator (tests/golden/make_reference_golden.py) and a CPU test that is
+skipped when the directory is missing call this.
+"""
+import importlib
+import os
+import sys
+import types
+
+from . import xarray_shim, xhistogram_shim
+
+
+def _module(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    return m
+
+
+def install():
+    """Register the stand-ins under the names the reference imports."""
+    def unavailable(*a, **k):
+        raise NotImplementedError("outside the hot path: not provided by oracle/refshim")
+    if "xarray" not in sys.modules:
+        sys.modules["xarray"] = xarray_shim
+    if "xhistogram" not in sys.modules:
+        xh = _module("xhistogram")
+        xh.xarray = _module("xhistogram.xarray", histogram=xhistogram_shim.histogram)
+        sys.modules["xhistogram"] = xh
+        sys.modules["xhistogram.xarray"] = xh.xarray
+    if "skimage" not in sys.modules:
+        sk = _module("skimage")
+        sk.measure = _module("skimage.measure", find_contours=unavailable)
+        sys.modules["skimage"] = sk
+        sys.modules["skimage.measure"] = sk.measure
+    if "xgcm" not in sys.modules:
+        xg = _module("xgcm", Grid=unavailable)
+        xg.autogenerate = _module("xgcm.autogenerate", generate_grid_ds=unavailable)
+        sys.modules["xgcm"] = xg
+        sys.modules["xgcm.autogenerate"] = xg.autogenerate
+
+
+def load_reference(root="/root/reference"):
+    """Import the reference's `xcontour` package from `root` on top of the stand-ins."""
+    if not os.path.isfile(os.path.join(root, "xcontour", "core.py")):
+        raise FileNotFoundError("no reference checkout at %s" % root)
+    install()
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    return importlib.import_module("xcontour")

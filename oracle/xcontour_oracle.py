@@ -7,28 +7,36 @@ of ``bench.py`` may import it.  The product (``xcontour_b200``) never does: it
 calls hand-written CUDA through ``libxcb200.so`` and fails loudly without it.
 
 What it is: a plain-NumPy restatement of the reference's arithmetic, function by
-function, on bare ndarrays (the reference's xarray / xhistogram orchestration is
-not importable in this image -- xarray, xhistogram, dask, xgcm, skimage are all
-absent and there is no network).  Every function cites the reference lines it
-follows (paths relative to ``/root/reference``).
+function, on bare ndarrays.  Every function cites the reference lines it follows
+(paths relative to ``/root/reference``).  The reference cannot be imported as is in
+this image (xarray, xhistogram, dask, xgcm, skimage are absent and there is no
+network), but its own unmodified ``xcontour/core.py`` does run on the minimal
+stand-ins of ``oracle/refshim`` -- that is how the golden vectors were made.
 
 Parity status
 -------------
-* ``cal_contours``           -- PINNED: reproduces bit-for-bit the 36 printed fp32
-  values of ``notebooks/1.Keff_atmos.ipynb:102-119`` (tests/golden/contours_pv.json).
-  The golden vector discriminates the dtype-promotion rule: only NumPy-1.x
-  semantics (python-float * np.float32 scalar -> float64) reproduce it, so that
-  is what is restated here, explicitly, independent of the installed NumPy.
-* everything else            -- PARITY UNPINNED: the reference ships no numeric
-  assertion, golden file or runnable test for these paths and
-  cannot be executed here.  The restatement follows ``xcontour/core.py`` literally
-  and xhistogram 0.3.0's published algorithm (digitize with right=False, last
-  edge + 1e-8 in the edge dtype, out-of-range and NaN discarded, bincount
-  weights in fp64) for the one third-party step (``core.py:1284``, ``1307``).
-  Sanity anchors that do exist are checked in tests: branch "case 1" messages,
-  LWA colour range 0-28 on ``Data/barotropic_vorticity.nc``
-  (``notebooks/2.LWA_atmos.ipynb`` cell 5), hist-vs-strict agreement
-  (``tests/test_hist.py:132-167``), brute-force vs reformulated LWA.
+* PINNED to the reference's own code: ``tests/golden/ref_*.npz`` hold inputs and
+  outputs of the unmodified reference (levels, histogram/CDF incl. the per-'time'
+  loop, both tables, lookups, d/dA, Leq2, nkeff, along-contour means, levels at
+  prescribed coordinates, np.interp to the grid, LWA / LAPE for every part, variant 2
+  and the integer masks; four (increase, lt) combinations; NaN cells, repeated values,
+  a decreasing X-Z coordinate with topography) executed here through
+  ``oracle/refshim`` by ``tests/golden/make_reference_golden.py``.  This module
+  reproduces them BIT FOR BIT except for the strict broadcast path, which sums in fp32
+  and agrees to summation-order level (``tests/test_reference_golden.py``).
+* PINNED to the published numbers: ``cal_contours`` reproduces the 36 printed fp32
+  values of ``notebooks/1.Keff_atmos.ipynb:102-119`` (tests/golden/contours_pv.json),
+  and so does the reference run above.
+* NOT pinned (restated from published behaviour, no source in /root/reference): the
+  internals of xarray and of xhistogram 0.3.0 (digitize with right=False, last edge
+  + 1e-8 in the edge dtype, out-of-range and NaN discarded, bincount weights in fp64;
+  call sites ``core.py:1284``, ``1307``) as written down in ``oracle/refshim``; and
+  ``squared_gradient_latlon``, which has no counterpart in the reference.
+* NumPy regime: the reference was written for NumPy 1.x.  Its scalar-promotion rules
+  differ from NEP 50 (NumPy >= 2) in one place on this path, the fp64 ``step`` of
+  ``_histogram`` (see ``hist_edges``); ``scalar_rules="numpy1"`` (default, and what the
+  CUDA path implements by default) and ``"numpy2"`` (the regime the fixtures were
+  generated in; ``XCB200_NUMPY_RULES=numpy2`` in the product) restate both.
 
 Array conventions: a tracer is ``q[S, n0, n1]`` (S independent slices, the 2-D
 plane last); contour-space arrays are ``[S, N]``; ``dA`` is ``[n0, n1]``.
@@ -46,12 +54,12 @@ def cal_contours(q, levels, increase=True, dtype=np.float32):
 
     core.py:222-249.  ``mmin/mmax`` are NaN-skipping reductions over the plane
     (xarray ``.min(dim=...)``).  ``mylinspace`` (core.py:228-232) is evaluated per
-    slice through ``np.vectorize`` on NumPy *scalars*:
-        steps = (1.0/divisor) * (stop - start)     # f32 - f32 -> f32, then python
-                                                   # float * f32 scalar -> f64 (NumPy 1.x)
+    slice through ``np.vectorize`` on NumPy *scalars* -- ``levels`` arrives as an
+    np.int64, so ``1.0/divisor`` is a float64 under NumPy 1.x and 2.x alike:
+        steps = (1.0/divisor) * (stop - start)     # f32 - f32 -> f32, then f64 * f32 -> f64
         steps * arange(levels) + start             # f64
-    and cast to ``self.dtype`` by ``output_dtypes`` (core.py:246).  The NumPy-1.x
-    promotion is pinned by the notebook golden vector (see module docstring).
+    and cast to ``self.dtype`` by ``output_dtypes`` (core.py:246).  Pinned by the
+    notebook golden vector and by the reference run of tests/golden/ref_vort32.npz.
     An array ``levels`` is broadcast verbatim (core.py:253-264).
     """
     q = np.asarray(q)
@@ -80,7 +88,7 @@ def contour_coord(N, dtype=np.float32):
 # --------------------------------------------------------------------------
 # histogram / CDF                       xcontour/core.py:412-460, 1202-1325
 # --------------------------------------------------------------------------
-def hist_edges(ctr, time_branch=True):
+def hist_edges(ctr, time_branch=True, scalar_rules="numpy1"):
     """Bin edges the reference hands to xhistogram for one slice.
 
     One extra bin below the smallest level so the result has N entries;
@@ -94,17 +102,25 @@ def hist_edges(ctr, time_branch=True):
 
     In both, ``step = (c_last - c_first) / (len - 1)`` is a NumPy scalar of the
     contour dtype divided by a Python int, i.e. fp64 under the NumPy-1.x scalar
-    rules the reference was written for (the same rules the golden contour
-    vector pins, see module docstring); restated explicitly here.
+    rules the reference was written for (README.md:26 states numpy 1.15.4);
+    restated explicitly here.
+    ``scalar_rules="numpy2"`` restates the same lines under NEP 50 (NumPy >= 2: the
+    step stays in the contour dtype, so both branches keep the contour dtype) --
+    the regime in which tests/golden/ref_*.npz were generated from the reference's
+    own code (tests/golden/make_reference_golden.py).
     Returns (edges[N+1] ascending, bincrease).
     """
     ctr = np.asarray(ctr)
     N = ctr.shape[0]
     bincrease = bool(ctr[0] < ctr[-1])
     first, last = (ctr[0], ctr[-1]) if bincrease else (ctr[-1], ctr[0])
+    body = ctr if bincrease else ctr[::-1]
+    if scalar_rules == "numpy2":
+        step = (last - first) / ctr.dtype.type(N - 1)  # scalar of ctr.dtype / python int
+        return np.concatenate([np.array([first - step], dtype=ctr.dtype), body]), bincrease
+    assert scalar_rules == "numpy1", scalar_rules
     step = np.float64(last - first) / (N - 1)          # difference in ctr.dtype
     e0 = np.float64(first) - step
-    body = ctr if bincrease else ctr[::-1]
     if time_branch:
         edges = np.concatenate([[e0], body.astype(np.float64)])
     else:
@@ -142,10 +158,10 @@ def digitize_bins(x, edges):
     return out.reshape(np.shape(x))
 
 
-def histogram_cdf(x, ctr, weights, lt, time_branch=True):
+def histogram_cdf(x, ctr, weights, lt, time_branch=True, scalar_rules="numpy1"):
     """``_histogram`` for one slice (core.py:1262-1325), in *storage* order
     (ascending bin values), plus ``bincrease``."""
-    edges, bincrease = hist_edges(ctr, time_branch)
+    edges, bincrease = hist_edges(ctr, time_branch, scalar_rules)
     pdf = xhistogram_1d(x, edges, weights)
     cdf = np.cumsum(pdf)                               # core.py:1320
     if not lt:
@@ -153,7 +169,8 @@ def histogram_cdf(x, ctr, weights, lt, time_branch=True):
     return cdf, bincrease
 
 
-def cal_integral_within_contours_hist(q, ctr, dA, lt, integrand=None, time_branch=None):
+def cal_integral_within_contours_hist(q, ctr, dA, lt, integrand=None, time_branch=None,
+                                      scalar_rules="numpy1"):
     """core.py:412-460.  ``wei = integrand*dA`` rounded in the operands' common
     dtype (core.py:444), ``fillna(0)`` (449), per-slice histogram CDF, then flip
     so that the contour index ascends (454-455).  The reference loops only over a
@@ -172,7 +189,7 @@ def cal_integral_within_contours_hist(q, ctr, dA, lt, integrand=None, time_branc
         else:
             wei = np.asarray(dA)
         wei = np.where(np.isnan(wei), 0.0, wei).astype(wei.dtype)
-        cdf, binc = histogram_cdf(q[s], c, wei, lt, time_branch)
+        cdf, binc = histogram_cdf(q[s], c, wei, lt, time_branch, scalar_rules)
         out[s] = cdf if binc else cdf[::-1]
     return out
 
@@ -206,7 +223,7 @@ def cal_integral_within_contours(q, ctr, dA, lt, integrand=None, chunk=16):
 # --------------------------------------------------------------------------
 # A(Yeq) table and lookups              xcontour/core.py:150-203, 1103-1174
 # --------------------------------------------------------------------------
-def cal_area_eqCoord_table_hist(coord, mask, dA, eq_axis, increase, lt):
+def cal_area_eqCoord_table_hist(coord, mask, dA, eq_axis, increase, lt, scalar_rules="numpy1"):
     """core.py:150-203.  Histogram of the eq-coordinate field (NaN where
     ``mask != 1``, core.py:178) against bins = the coordinate vector with weights
     ``dA``; ``ylt = lt if increase == yIncre else not lt`` (180-188).  The table
@@ -220,7 +237,7 @@ def cal_area_eqCoord_table_hist(coord, mask, dA, eq_axis, increase, lt):
     ctrVar = np.where(mask == 1, ctrVar, np.nan)
     yIncre = not (coord[-1] < coord[0])
     ylt = lt if (increase == yIncre) else (not lt)
-    cdf, _ = histogram_cdf(ctrVar, coord, dA, ylt, time_branch=False)
+    cdf, _ = histogram_cdf(ctrVar, coord, dA, ylt, time_branch=False, scalar_rules=scalar_rules)
     coord_asc = coord if yIncre else coord[::-1]
     return cdf, coord_asc.copy()
 
@@ -403,20 +420,24 @@ def cal_local_wave_activity(q, Q, dA, coord, increase, part="all",
     out = np.zeros((S, ny, nx), dtype=np.float64)
     contours, masks = [], []
     for j in jj:
-        if variant == 1:
-            qe = q - Q[:, j][:, None, None]              # core.py:754
-            inc_flag = increase
-        else:
-            qe = q[:, j, :][:, None, :] - Q[:, :, None]  # core.py:860
-            inc_flag = not increase                      # core.py:865-872
         m = (coord >= coord[j]) if coord_incre else (coord <= coord[j])
-        m = m[None, :, None]
-        mask3 = _lwa_masks(qe, m, inc_flag)
+        if variant == 1:
+            qe = q - Q[:, j][:, None, None]              # core.py:754, dims (S, eq, x)
+            mask3 = _lwa_masks(qe, m[None, :, None], increase)
+            mf = _select_part(mask3, part, increase)
+            lwa = -np.nansum(qe * mf * wei[None] * dA[None], axis=1)
+        else:
+            # core.py:860: q.isel(eq=j) - Q broadcasts to dims (S, x, eq) -- the eq axis
+            # comes LAST, which is the order the terms are summed in (core.py:865-872, 896)
+            qe = q[:, j, :][:, :, None] - Q[:, None, :]
+            mask3 = _lwa_masks(qe, m[None, None, :], not increase)
+            mf = _select_part(mask3, part, increase)
+            lwa = -np.nansum(qe * mf * wei.T[None] * dA.T[None], axis=2)
+            mask3 = mask3.transpose(0, 2, 1)
         if mask_idx is not None and j in mask_idx:
             contours.append(Q[:, j].copy())
             masks.append(mask3.copy())
-        mf = _select_part(mask3, part, increase)
-        out[:, j, :] = -np.nansum(qe * mf * wei[None] * dA[None], axis=1)
+        out[:, j, :] = lwa
     if mask_idx is not None:
         return out, contours, masks
     return out

@@ -37,8 +37,11 @@ def test_contours_golden_notebook():
 
 
 def test_contours_promotion_rule_is_discriminated():
-    """The NEP-50 (NumPy 2) evaluation of the same expression does NOT reproduce
-    the golden vector; this is why the oracle restates the NumPy-1.x rule."""
+    """An all-fp32 evaluation of the steps does NOT reproduce the golden vector: the
+    levels are computed in fp64 (np.vectorize hands `levels` over as np.int64, so
+    `1.0/divisor` is a float64) and rounded to fp32 once, which is what the oracle
+    restates and what the reference's own code returns when run here
+    (tests/test_reference_golden.py)."""
     g = json.load(open(os.path.join(GOLDEN, "contours_pv.json")))
     N, mism = g["levels_N"], 0
     for row in g["printed"]:
