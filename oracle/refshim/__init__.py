@@ -16,6 +16,7 @@ the fixture generator (tests/golden/make_reference_golden.py) and a CPU test tha
 skipped when the directory is missing call this.
 """
 import importlib
+import importlib.util
 import os
 import sys
 import types
@@ -57,6 +58,19 @@ def load_reference(root="/root/reference"):
     if not os.path.isfile(os.path.join(root, "xcontour", "core.py")):
         raise FileNotFoundError("no reference checkout at %s" % root)
     install()
-    if root not in sys.path:
-        sys.path.insert(0, root)
-    return importlib.import_module("xcontour")
+    if "xcontour" in sys.modules:
+        return sys.modules["xcontour"]
+    pkg = os.path.join(root, "xcontour")
+    spec = importlib.util.spec_from_file_location("xcontour", os.path.join(pkg, "__init__.py"),
+                                                  submodule_search_locations=[pkg])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["xcontour"] = mod
+    nobytecode, sys.dont_write_bytecode = sys.dont_write_bytecode, True     # the mount is read-only
+    try:
+        spec.loader.exec_module(mod)
+    except BaseException:
+        sys.modules.pop("xcontour", None)
+        raise
+    finally:
+        sys.dont_write_bytecode = nobytecode
+    return mod
