@@ -187,7 +187,7 @@ def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from xcontour_b200 import ops
     from xcontour_b200._lib import N_STAGES, STAGE_NAMES
-    from xcontour_b200.pipeline import HostStreamer, KeffLwaPlan
+    from xcontour_b200.pipeline import HostStreamer, KeffLwaPlan, bind_host_thread_to_gpu
     from xcontour_b200.utils import latlon_cell_area
 
     torch.cuda.set_device(local_rank)
@@ -280,6 +280,8 @@ def run_ours(args, rank, world, local_rank):
 
     # end to end: pinned host slices -> H2D -> fused batch -> D2H of every result
     eb = min(args.e2e_batch, B)
+    # pinned buffers are first-touched on the GPU's own NUMA node (undone after this leg)
+    prev_aff, numa_note = (None, "off") if args.no_numa else bind_host_thread_to_gpu(local_rank)
     streamer = HostStreamer(plan, eb, copy_lwa=True, nbuf=args.e2e_nbuf)
     q_host = torch.empty((B, NY, NX), dtype=torch.float32).pin_memory()
     q_host.copy_(q)
@@ -308,6 +310,8 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B * e2e_steps / float(te.item())
+    if prev_aff is not None:
+        os.sched_setaffinity(0, prev_aff)                        # the cpu_baseline leg uses every core
 
     if rank == 0:
         peak, peak_src = peak_hbm()
@@ -344,7 +348,7 @@ def run_ours(args, rank, world, local_rank):
                     "h2d_bytes_per_step": streamer.h2d_bytes // e2e_steps,
                     "d2h_bytes_per_step": streamer.d2h_bytes // e2e_steps,
                     "timing": "CUDA events spanning pinned H2D + kernels + D2H on both streams, max over ranks",
-                    "batch": eb, "buffers_in_flight": args.e2e_nbuf},
+                    "batch": eb, "buffers_in_flight": args.e2e_nbuf, "host_numa": numa_note},
             "gpu_launches": int(launches) * world,
         }
         if world == 1 and not args.no_cpu:
@@ -368,6 +372,7 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=8)
     ap.add_argument("--e2e-nbuf", type=int, default=2, help="batches in flight in the end-to-end leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the end-to-end leg's host thread to the GPU's NUMA node")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -119,6 +119,52 @@ class KeffLwaPlan(object):
         return out
 
 
+def bind_host_thread_to_gpu(device_index=None):
+    """Restrict the calling host thread to the CPUs NVML reports as local to the GPU
+    (its NUMA node), so that pinned host buffers allocated afterwards are first-touched
+    in the memory that GPU's PCIe root complex reaches without crossing the socket
+    interconnect -- on an 8-GPU box that is what the end-to-end (host-buffer) path is
+    bound by once every rank streams at PCIe rate.  Best effort: returns
+    ``(previous_affinity, description)`` and never raises; ``previous_affinity`` is None
+    when nothing was changed.  Undo with ``os.sched_setaffinity(0, previous_affinity)``."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        idx = torch.cuda.current_device() if device_index is None else int(device_index)
+        props = torch.cuda.get_device_properties(idx)
+        h = None
+        uuid = getattr(props, "uuid", None)
+        if uuid is not None:
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(uuid))
+            except Exception:
+                h = None
+        if h is None and hasattr(props, "pci_bus_id"):
+            try:
+                h = pynvml.nvmlDeviceGetHandleByPciBusId("%08x:%02x:%02x.0" % (
+                    getattr(props, "pci_domain_id", 0), props.pci_bus_id, getattr(props, "pci_device_id", 0)))
+            except Exception:
+                h = None
+        if h is None:
+            return None, "no NVML handle for cuda:%d" % idx
+        allowed = os.sched_getaffinity(0)
+        ncpu = max(allowed) + 1 if allowed else (os.cpu_count() or 1)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(ncpu, os.cpu_count() or 1) + 63) // 64)
+        local = set(64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1)
+        try:
+            node = int(pynvml.nvmlDeviceGetNumaNodeId(h))
+        except Exception:
+            node = None
+        target = local & allowed
+        if not target or target == allowed:
+            return None, "numa node %s: %d local cpus, %d allowed, affinity unchanged" % (node, len(local), len(allowed))
+        os.sched_setaffinity(0, target)
+        return allowed, "numa node %s: bound to %d of %d allowed cpus" % (node, len(target), len(allowed))
+    except Exception as e:                                      # no NVML, no permission, ...
+        return None, "unavailable (%s)" % type(e).__name__
+
+
 class HostStreamer(object):
     """End-to-end driver for HOST-resident tracers: pinned host slices ->
     (H2D, fused batch, D2H of every result) with ``nbuf`` buffers in flight so the
