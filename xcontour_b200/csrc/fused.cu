@@ -141,9 +141,13 @@ extern "C" int xc_keff_lwa_batch(const xc_keff_lwa_args* a, void* workspace, siz
     cudaStream_t st = (cudaStream_t)stream;
     const long npass = (S + pl.sub - 1) / pl.sub;
     // optional per-stage timing (forces the serial schedule so that stages do not overlap)
-    std::vector<cudaEvent_t> ev;
+    struct Events {                                      // destroyed on every return path
+        std::vector<cudaEvent_t> v;
+        ~Events() { for (cudaEvent_t e : v) if (e) cudaEventDestroy(e); }
+    } evs;
+    std::vector<cudaEvent_t>& ev = evs.v;
     if (a->stage_ms) {
-        ev.resize((size_t)npass * (XC_N_STAGES + 1));
+        ev.assign((size_t)npass * (XC_N_STAGES + 1), nullptr);
         for (auto& e : ev) XC_CUDA_OK(cudaEventCreate(&e));
     }
     // Two passes in flight: pass p runs start to finish on internal stream p % 2 with
@@ -217,7 +221,6 @@ extern "C" int xc_keff_lwa_batch(const xc_keff_lwa_args* a, void* workspace, siz
                 cudaEventElapsedTime(&ms, ev[(size_t)p * (XC_N_STAGES + 1) + k], ev[(size_t)p * (XC_N_STAGES + 1) + k + 1]);
                 a->stage_ms[k] += ms;
             }
-        for (auto& e : ev) cudaEventDestroy(e);
     }
     return 0;
 }
