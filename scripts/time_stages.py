@@ -21,7 +21,7 @@ for s in range(B):
         + float(os.environ.get("XC_NOISE", "0.02")) * torch.randn((bench.NY, bench.NX), generator=g, device="cuda")
 if os.environ.get("XC_QUANT"):      # pathological: large patches of identical values
     k = float(os.environ["XC_QUANT"]); q = torch.round(q * k) / k
-out = plan.alloc_outputs(B)
+out = plan.alloc_outputs(B, lwa=not os.environ.get("XC_NO_LWA"))
 for _ in range(3):
     plan.run(q, out=out)
 torch.cuda.synchronize()

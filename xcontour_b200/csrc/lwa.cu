@@ -500,6 +500,16 @@ __device__ __forceinline__ void fx_value(double qraw, float, double sg, double& 
 #ifndef XC_FX_PROBES
 #define XC_FX_PROBES 2
 #endif
+#ifndef XC_FX_EXP            /* timing-split builds only (results wrong by construction): 1 = scatter phase without
+                                its shared-memory atomics, 2 = no scatter phase at all (scripts/lwa_split.sh) */
+#define XC_FX_EXP 0
+#endif
+#ifndef XC_FX_OWN            /* 1: the +X deposit at the cell's own slot is made with shared-memory atomics in the
+                                scatter phase instead of being re-derived from (q, ww) in the prefix phase.  Measured
+                                split (profiles/r1_time_split.txt): the four atomics of a cell cost 5 % of the kernel,
+                                the prefix side 64 % -- candidate for round 2, not yet timed (scripts/ab_round2.sh). */
+#define XC_FX_OWN 0
+#endif
 constexpr int FX_U = XC_FX_U;        // rows whose loads are in flight together
 
 template <typename QT, int FX_TC>
@@ -556,7 +566,7 @@ k_lwa_fx(const QT* __restrict__ q, long s0, long sbase, int ny, int nx,
 
     // ---- scatter: one deposit of -X at the far end of each cell's range ----
     long long ownS = 0, ownV = 0;
-    if (col_ok) {
+    if (col_ok && XC_FX_EXP != 2) {
         const double nsS = -fsS, nsV = -fsV;
         const QT* qp = qc; const double* wp = wc;
         for (int jb = r0; jb < r1; jb += FX_U) {
@@ -591,10 +601,23 @@ k_lwa_fx(const QT* __restrict__ q, long s0, long sbase, int ny, int nx,
                     }
                     if (h <= jp && use_t2) target = h;
                 }
+#if XC_FX_OWN
+                if (target == jp + 1) continue;                  // inactive: nothing to deposit
+                {
+                    uint32_t* so = fcol + (jp + 1) * FX_TC;      // +X at the own slot
+                    fx_add64(so, so + plane, 0, -NS);
+                    fx_add64(so + 2 * plane, so + 3 * plane, 0, -NV);
+                }
+#else
                 ownS -= NS; ownV -= NV;
+#endif
                 uint32_t* slot = fcol + target * FX_TC;
+#if XC_FX_EXP == 1
+                ownS += (long long)(slot - far);                 // keeps the search alive without touching shared memory
+#else
                 fx_add64(slot, slot + plane, 0, NS);
                 fx_add64(slot + 2 * plane, slot + 3 * plane, 0, NV);
+#endif
             }
         }
     }
@@ -628,6 +651,16 @@ k_lwa_fx(const QT* __restrict__ q, long s0, long sbase, int ny, int nx,
         const QT* qp = qc; const double* wp = wc;
         const uint32_t* sl = fcol + r0 * FX_TC;
         const double* Qj = Qs + r0;
+#if XC_FX_OWN
+        for (int j = r0; j < r1; ++j) {                          // every deposit is in the planes: a plain inclusive prefix
+            RS += (long long)(((unsigned long long)sl[plane] << 32) | sl[0]);
+            RV += (long long)(((unsigned long long)sl[3 * plane] << 32) | sl[2 * plane]);
+            const double Sj = __dmul_rn(fx_to_double(RS), fiS), Vj = __dmul_rn(fx_to_double(RV), fiV);
+            *op = sg * (Vj - (*Qj - fc) * Sj);
+            op += nx; sl += FX_TC; ++Qj;
+        }
+        (void)qc; (void)wc;
+#else
         for (int jb = r0; jb < r1; jb += FX_U) {
             QT qv[FX_U]; double wv[FX_U];
 #pragma unroll
@@ -654,6 +687,7 @@ k_lwa_fx(const QT* __restrict__ q, long s0, long sbase, int ny, int nx,
                 }
             }
         }
+#endif
     }
 }
 
