@@ -278,3 +278,58 @@ def test_product_matches_reference_fixtures(case, monkeypatch):
         lwa2, cs2, ms2 = an.cal_local_wave_activity2(tr, Q, mask_idx=idx, part="all")
         assert _relmax(lwa2.values, want["lwa2_all"]) <= 1e-10
         assert np.array_equal(np.stack([np.asarray(m.values) for m in ms2]).astype(np.int8), want["lwa2_masks"])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/xcontour"), reason="reference checkout not present")
+@pytest.mark.parametrize("increase,lt", [(True, True), (False, False)])
+def test_oracle_equals_reference_on_the_full_vorticity_field(vort, increase, lt):
+    """Not a stored fixture (the fields are too large to commit): the reference's own code,
+    run here on the full 256x512 Data/barotropic_vorticity.nc field with N = 121 (the setup of
+    tests/test_LWA.py), against the oracle -- bit for bit, Keff chain and LWA."""
+    code = r'''
+import sys, numpy as np
+sys.dont_write_bytecode = True
+sys.path.insert(0, %r)
+from oracle import refshim, xcontour_oracle as O
+ref = refshim.load_reference("/root/reference")
+import xarray as xr
+d = np.load(%r)
+lat, lon, q = d["latitude"], d["longitude"], d["absolute_vorticity"]
+increase, lt, N = %r, %r, 121
+dA = O.latlon_cell_area(lat, lon).astype(np.float32)
+grd = O.squared_gradient_latlon(q, lat, lon).astype(np.float32)
+co = {"Y": lat, "X": lon}
+tr = xr.DataArray(q, dims=("Y", "X"), coords=co, name="vor")
+gx = xr.DataArray(grd, dims=("Y", "X"), coords=co, name="grdS")
+an = ref.Contour2D(tr, xr.DataArray(dA, dims=("Y", "X"), coords=co), dims={"X": "X", "Y": "Y"},
+                   dimEq={"Y": "Y"}, increase=increase, lt=lt)
+ctr = an.cal_contours(N)
+table = an.cal_area_eqCoord_table_hist(xr.DataArray(np.ones_like(q), dims=("Y", "X"), coords=co, name="m"))
+area = an.cal_integral_within_contours_hist(ctr).rename("intArea")
+intg = an.cal_integral_within_contours_hist(ctr, integrand=gx).rename("intgrdS")
+latEq = table.lookup_coordinates(area).rename("latEq")
+nk = an.cal_normalized_Keff(an.cal_sqared_equivalent_length(an.cal_gradient_wrt_area(intg, area),
+                                                            an.cal_gradient_wrt_area(ctr, area)),
+                            ref.latitude_lengths_at(latEq))
+Q = an.interp_to_dataset(tr["Y"].astype(np.float32), latEq, [ctr, area, latEq])["vor"]
+lwa = an.cal_local_wave_activity(tr, Q)
+q3 = q[None]
+o_ctr = O.cal_contours(q3, N, increase)
+tbl, c = O.cal_area_eqCoord_table_hist(lat, np.ones_like(q), dA, 0, increase, lt)
+o_area = O.cal_integral_within_contours_hist(q3, o_ctr[0], dA, lt, time_branch=False)
+o_intg = O.cal_integral_within_contours_hist(q3, o_ctr[0], dA, lt, integrand=grd[None], time_branch=False)
+o_latEq = O.table_lookup_coordinates(o_area, tbl, c)
+with np.errstate(all="ignore"):
+    o_nk = O.cal_normalized_Keff(O.cal_sqared_equivalent_length(O.cal_gradient_wrt_area(o_intg, o_area),
+                                                                O.cal_gradient_wrt_area(o_ctr, o_area)),
+                                 O.latitude_lengths_at(o_latEq))
+o_Q = O.interp_to_coords(lat, o_latEq, o_ctr)
+o_lwa = O.cal_local_wave_activity(q3, o_Q, dA, lat, increase)
+for name, a, b in (("ctr", ctr.values, o_ctr[0]), ("area", area.values, o_area[0]), ("intgrdS", intg.values, o_intg[0]),
+                   ("latEq", latEq.values, o_latEq[0]), ("nkeff", nk.values, o_nk[0]), ("Q", Q.values, o_Q[0]),
+                   ("lwa", lwa.values, o_lwa[0])):
+    assert a.dtype == b.dtype and np.array_equal(a, b, equal_nan=True), name
+print("identical")
+''' % (ROOT, os.path.join(GOLDEN, "barotropic_vorticity.npz"), increase, lt)
+    r = subprocess.run([sys.executable, "-B", "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "identical" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
