@@ -15,7 +15,10 @@ import pytest
 from oracle import xcontour_oracle as O
 
 
-def lwa_fixed_point_model(q3, Q, dA, increase, part):
+def lwa_fixed_point_model(q3, Q, dA, increase, part, own_in_planes=False):
+    """own_in_planes=True models the -DXC_FX_OWN=1 build: the +X deposit goes to slot j'+1 of
+    the planes in the scatter phase (inactive cells deposit nothing) and the walk is a plain
+    inclusive prefix."""
     S, ny, nx = q3.shape
     sg = 1.0 if increase else -1.0
     dAmax = np.nanmax(dA)
@@ -52,9 +55,16 @@ def lwa_fixed_point_model(q3, Q, dA, increase, part):
                     t = lo if use_t1 else t
                 elif hi <= jp and use_t2:
                     t = hi
+                if own_in_planes:
+                    own.append((0, 0))
+                    if t == jp + 1:
+                        continue
+                    far_S[jp + 1] += XS
+                    far_V[jp + 1] += XV
+                else:
+                    own.append((XS, XV))
                 far_S[t] -= XS
                 far_V[t] -= XV
-                own.append((XS, XV))
             RS = RV = 0
             for j in range(ny):
                 RS += far_S[j]
@@ -86,6 +96,8 @@ def test_lwa_fixed_point_model_matches_reference_loop(increase, part):
     out = lwa_fixed_point_model(q3, Q, dA, increase, part)
     for s in range(2):
         assert np.abs(out[s] - ref[s]).max() <= 1e-12 * np.abs(ref[s]).max()
+    # the prepared variant (own-slot deposits in the planes) sums the same integers
+    assert np.array_equal(lwa_fixed_point_model(q3, Q, dA, increase, part, own_in_planes=True), out)
 
 
 HKX_NW, HKX_WBITS, HKX_MARGIN = 6, 24, 12
