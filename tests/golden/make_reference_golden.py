@@ -157,6 +157,10 @@ def _run_chain(ref, xr, inp, eq, lead, increase, lt, out, with_grd=True, parts=(
             predef = np.linspace(float(inp[eq][2]), float(inp[eq][-3]), 11).astype(np.float32)
             out[t + "/ctr_at_hist"] = an.cal_contours_at_hist(predef, table).values
             out[t + "/ctr_at_predef"] = predef
+            # the conditional-integration twins (fp32 sums in the reference)
+            out[t + "/lwm_strict"] = an.cal_contour_weigh_mean(ctr, gx).values
+            out[t + "/cm_strict"] = an.cal_contour_mean(ctr, tr, gx).values
+            out[t + "/ctr_at_strict"] = an.cal_contours_at(predef, an.cal_area_eqCoord_table(mk)).values
     if strict:
         out[t + "/table_strict"] = an.cal_area_eqCoord_table(mk)._table.values
         out[t + "/area_strict"] = an.cal_integral_within_contours(ctr).values
