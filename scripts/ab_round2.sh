@@ -1,17 +1,28 @@
-# Round-2 starting point: A/B of the prepared k_lwa_fx variant (XC_FX_OWN=1: own-slot deposits made with
-# shared-memory atomics, prefix phase without global loads -- see DESIGN.md §8 and profiles/r1_time_split.txt).
+# Round-2 starting point: A/B of the variants prepared (and not yet timed) at the end of round 1.  Every one is a
+# compile-time switch whose default leaves the round-1 SASS untouched (profiles/README.md):
+#   own    -DXC_FX_OWN=1     k_lwa_fx: own-slot deposits with shared-memory atomics, prefix walk without global loads
+#   lut4k  -DXC_FX_LUT=4096  k_lwa_fx: 4x finer LUT over Q (the closing bisection is 9 % of the kernel's instructions)
+#   lean   -DXC_HKX_LEAN=1   k_hist_keff: funnel-shift decomposition, out-of-line truncation, 64-bit-add carries,
+#                            no division in the cell loop (hkx_add is 55 % of the kernel's instructions)
+#   all    the three together
 #
 #   1. on the CPU (build container):
-#        python -c "from xcontour_b200 import build as b; b.build(variant='own', defines=['XC_FX_OWN=1'])"
-#   2. on the GPU:   gpurun --timeout 300 -- 'bash scripts/ab_round2.sh'
+#        python scripts/build_variants.py own:XC_FX_OWN=1 lut4k:XC_FX_LUT=4096 lean:XC_HKX_LEAN=1 \
+#               all:XC_FX_OWN=1,XC_FX_LUT=4096,XC_HKX_LEAN=1
+#   2. on the GPU:   gpurun --timeout 600 -- 'bash scripts/ab_round2.sh'
 #
-# The variant is held to the full parity suite first (XCB200_LIB selects the library for every test), then
-# timed stage by stage against the default build on the benchmark field, a smooth one and a quantised one.
+# Each variant is first held to the parity tests that touch its kernel (XCB200_LIB selects the library for every
+# test; run the whole suite on the winner before flipping a default), then timed stage by stage against the default
+# build on the benchmark field, a smooth one and a quantised one.
 mkdir -p gpurun_out
-L=$PWD/xcontour_b200/libxcb200_own.so
-( XCB200_LIB=$L timeout 200 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+D=$PWD/xcontour_b200
+( for v in own lut4k lean all; do
+    echo "== parity, variant $v"
+    XCB200_LIB=$D/libxcb200_$v.so timeout 300 python -m pytest tests -m gpu -x -q \
+        -k "lwa or lape or fused or workflow or reference_fixtures or full_size or cdf or hist or keff or accumulators or smoke" 2>&1 | tail -2
+  done
   for env in "" "XC_NOISE=0" "XC_QUANT=8"; do
     echo "== field: ${env:-benchmark}"
     env $env python scripts/time_stages.py 32 32
-    env $env XCB200_LIB=$L python scripts/time_stages.py 32 32
-  done ) 2>&1 | grep -v Warning | tee gpurun_out/r2_ab_own.txt
+    for v in own lut4k lean all; do env $env XCB200_LIB=$D/libxcb200_$v.so python scripts/time_stages.py 32 32; done
+  done ) 2>&1 | grep -v Warning | tee gpurun_out/r2_ab.txt

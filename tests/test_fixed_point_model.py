@@ -147,3 +147,18 @@ def test_windowed_accumulators_are_exact_over_120_binary_orders():
     # negative, infinite and huge terms take the side table
     assert windowed_sum_model([1.0, -0.25, 2.0 ** 300]) == 1.0 - 0.25 + 2.0 ** 300
     assert math.isinf(windowed_sum_model([1.0, math.inf]))
+
+
+def test_lean_term_decomposition_equals_the_default(tmp_path):
+    """xcontour_b200/csrc/hkx_decompose.cuh compiled for the CPU: the funnel-shift decomposition of the
+    prepared -DXC_HKX_LEAN=1 build returns the same (window, 96-bit value) as the default statement for
+    20 million terms (random bit patterns, exponents around the window range, anchors over the whole
+    exponent range)."""
+    import os, shutil, subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no host compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "hkx_decompose_test")
+    subprocess.check_call(["g++", "-O2", "-o", exe, os.path.join(root, "tests", "host", "hkx_decompose_test.cpp")])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and " 0 mismatches" in r.stdout, r.stdout[-500:]

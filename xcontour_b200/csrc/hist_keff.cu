@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "internal.h"
 #include "grad2.cuh"
+#include "hkx_decompose.cuh"
 #include <math_constants.h>
 
 namespace xc {
@@ -143,6 +144,46 @@ constexpr int HKX_MARGIN = 12;           // windows start this many bits below t
                                 weights are computed but nothing is accumulated (scripts/lwa_split.sh) */
 #define XC_HKX_EXP 0
 #endif
+#ifndef XC_HKX_LEAN          /* 1: same sums from fewer instructions -- 32-bit funnel shifts instead of 64-bit variable
+                                shifts (hkx_decompose.cuh, checked on the CPU against the default statement), the
+                                below-anchor truncation out of line, carries from 64-bit adds, no division in the cell
+                                loop.  The ncu source page of the default build puts 55 % of the kernel's instructions
+                                in hkx_add, 8 % of them in the (never taken) truncation alone.  Candidate for round 2,
+                                not yet timed (scripts/ab_round2.sh). */
+#define XC_HKX_LEAN 0
+#endif
+#if XC_HKX_LEAN
+__device__ __noinline__ unsigned long long hkx_shift_below(unsigned long long m, int rel)
+{
+    return rel > -53 ? (m >> (-rel)) : 0ull;
+}
+__device__ __forceinline__ void hkx_add(uint32_t* acc, double* esc, int N, int bin, int e_base, double x)
+{
+    const int hi = __double2hiint(x);
+    const uint32_t lo = (uint32_t)__double2loint(x);
+    const int ex = (hi >> 20) & 0x7ff;
+    int rel = ex - e_base;
+    if (hi < 0 || ex == 0x7ff || ex == 0 || rel >= HKX_NW * HKX_WBITS) {
+        if (x != 0.0) atomicAdd(esc + bin, x);
+        return;
+    }
+    uint32_t mh = (uint32_t)((hi & 0xfffff) | 0x100000), ml = lo;
+    if (rel < 0) {                                           // below the anchor: a real branch, never taken on sane data
+        const unsigned long long r = hkx_shift_below(((unsigned long long)mh << 32) | ml, rel);
+        mh = (uint32_t)(r >> 32); ml = (uint32_t)r; rel = 0;
+    }
+    const int w = (rel * 2731) >> 16;
+    const int sh = rel - w * HKX_WBITS;
+    const uint32_t v0 = ml << sh, v1 = __funnelshift_l(ml, mh, sh), v2 = __funnelshift_l(mh, 0u, sh);
+    uint32_t* s = acc + ((size_t)w * N + bin) * 3;
+    const uint32_t o0 = atomicAdd(s, v0);
+    const unsigned long long t0 = (unsigned long long)o0 + v0;                   // bit 32: carry out of word 0
+    const unsigned long long t1 = (unsigned long long)v1 + (uint32_t)(t0 >> 32);
+    const uint32_t o1 = atomicAdd(s + 1, (uint32_t)t1);
+    const unsigned long long u1 = (unsigned long long)o1 + (uint32_t)t1;
+    atomicAdd(s + 2, v2 + (uint32_t)(t1 >> 32) + (uint32_t)(u1 >> 32));
+}
+#else
 __device__ __forceinline__ void hkx_add(uint32_t* acc, double* esc, int N, int bin, int e_base, double x)
 {
 #if XC_HKX_EXP == 1
@@ -172,6 +213,7 @@ __device__ __forceinline__ void hkx_add(uint32_t* acc, double* esc, int N, int b
     const uint32_t c1 = (uint32_t)(t1 < c0) + (uint32_t)((o1 + t1) < t1);
     atomicAdd(s + 2, v2 + c1);
 }
+#endif
 // exponent field of a term that can anchor the windows (positive, finite, normal), else INT_MAX
 __device__ __forceinline__ int hkx_exp(double x)
 {
@@ -268,6 +310,10 @@ k_hist_keff(const HistKeffParams p)
     // (FX) every warp of the CTA takes part in the first step -- `per` is a multiple of HK_WARPS*128 or the
     // loop bound below is padded so that the anchoring barrier is reached by all threads
     const int end_it = FX ? beg + ((end - beg + HK_WARPS * 128 - 1) / (HK_WARPS * 128)) * (HK_WARPS * 128) : end;
+#if XC_HKX_LEAN
+    const bool walk = nx >= HK_WARPS * 128;             // then a step crosses at most one row boundary
+    int jw = (beg + warp * 128 + lane * 4) / nx, cw = (beg + warp * 128 + lane * 4) - jw * nx;
+#endif
     for (int base = beg + warp * 128; base < end_it; base += HK_WARPS * 128) {
         const int i0 = base + lane * 4;
         const bool ok = i0 < end;                       // P, per and nx are multiples of 4: all-or-nothing
@@ -275,7 +321,12 @@ k_hist_keff(const HistKeffParams p)
         float4 qc = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F), a4 = qc, nn = qc, ss = qc;
         float wv = 0.f, ev = 0.f; double cx = 0.0, cy = 0.0;
         if (ok) {
+#if XC_HKX_LEAN
+            if (walk) { j = jw; col = cw; cw += HK_WARPS * 128; if (cw >= nx) { cw -= nx; ++jw; } }
+            else { j = i0 / nx; col = i0 - j * nx; }
+#else
             j = i0 / nx; col = i0 - j * nx;
+#endif
             const float* row = qs + (long)j * nx;
             const int jm = j == 0 ? 0 : j - 1, jp = j == ny - 1 ? ny - 1 : j + 1;
             qc = __ldg(reinterpret_cast<const float4*>(row + col));

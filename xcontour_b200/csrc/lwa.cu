@@ -377,8 +377,13 @@ k_lwa_fast(const QT* __restrict__ q, long s0, int ny, int nx,
 // Two tile shapes: 16 columns x 1024 threads (one CTA per SM; a warp-wide global
 // access then covers 2 rows x 64/128 B instead of 4 rows x 32/64 B, which is what
 // the LSU data pipe is paid in) while the four planes fit 227 KB, else 8 x 512.
+#ifndef XC_FX_LUT            /* buckets of the LUT over Q.  The bisection that finishes the search is the most
+                                expensive source line of the kernel (9 % of its instructions, ncu source page); 4096
+                                buckets still fit the 16-column tile at ny = 721 (224 of 227 KB).  Not yet timed. */
+#define XC_FX_LUT 1024
+#endif
 constexpr int FX_SEG = 64;                 // row segments per column (threads = FX_SEG * TC)
-constexpr int FX_LUT = 1024;
+constexpr int FX_LUT = XC_FX_LUT;
 constexpr int FX_TOTP = FX_SEG + 2;        // padded row of the totals table
 
 struct LwaFxSmem { size_t off_Q, off_far, off_lut, off_tot, total; int plane; };
