@@ -15,7 +15,7 @@ int main()
     long n = 0, acc = 0, bad = 0;
     for (long it = 0; it < 20000000; ++it) {
         uint64_t bits = next();
-        int e_base = 1 + (int)(next() % 2046);
+        int e_base = -11 + (int)(next() % 2070);                 // anchors as the kernel can produce them (>= 1 - 12) and beyond the top
         if (it % 3 == 0) {                                   // exponents around the window range
             const int ex = e_base - 60 + (int)(next() % (nw * wbits + 70));
             if (ex > 0 && ex < 0x7ff) bits = (bits & 0x800FFFFFFFFFFFFFull) | ((uint64_t)ex << 52);

@@ -161,12 +161,11 @@ __device__ __forceinline__ void hkx_add(uint32_t* acc, double* esc, int N, int b
 {
     const int hi = __double2hiint(x);
     const uint32_t lo = (uint32_t)__double2loint(x);
-    const int ex = (hi >> 20) & 0x7ff;
-    int rel = ex - e_base;
-    if (hi < 0 || ex == 0x7ff || ex == 0 || rel >= HKX_NW * HKX_WBITS) {
+    if ((uint32_t)hi - 0x00100000u >= hkx_accept_span(e_base, HKX_NW, HKX_WBITS)) {   // one comparison, see hkx_decompose.cuh
         if (x != 0.0) atomicAdd(esc + bin, x);
         return;
     }
+    int rel = (hi >> 20) - e_base;
     uint32_t mh = (uint32_t)((hi & 0xfffff) | 0x100000), ml = lo;
     if (rel < 0) {                                           // below the anchor: a real branch, never taken on sane data
         const unsigned long long r = hkx_shift_below(((unsigned long long)mh << 32) | ml, rel);

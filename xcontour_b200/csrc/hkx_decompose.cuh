@@ -41,11 +41,18 @@ HKX_HD uint32_t hkx_funnel_l(uint32_t lo, uint32_t hi, int sh)   // upper word o
 #endif
 }
 
+// Accepted terms are positive, normal, finite and below the top window: hi in
+// [0x00100000, min(0x7ff, e_base + nw*wbits) << 20) -- one unsigned comparison.
+HKX_HD uint32_t hkx_accept_span(int e_base, int nw, int wbits)
+{
+    const int top = e_base + nw * wbits;
+    return ((uint32_t)(top < 0x7ff ? (top > 1 ? top : 1) : 0x7ff) << 20) - 0x00100000u;
+}
+
 HKX_HD int hkx_decompose_lean(int hi, uint32_t lo, int e_base, int nw, int wbits, HkxTerm& t)
 {
-    const int ex = (hi >> 20) & 0x7ff;
-    int rel = ex - e_base;
-    if (hi < 0 || ex == 0x7ff || ex == 0 || rel >= nw * wbits) return 1;
+    if ((uint32_t)hi - 0x00100000u >= hkx_accept_span(e_base, nw, wbits)) return 1;
+    int rel = (hi >> 20) - e_base;                           // hi >= 0 here: no mask needed
     uint32_t mh = (uint32_t)((hi & 0xfffff) | 0x100000), ml = lo;
     if (rel < 0) {                                           // below the anchor: truncate (rare)
         const unsigned long long m = (((unsigned long long)mh << 32) | ml);

@@ -377,6 +377,9 @@ k_lwa_fast(const QT* __restrict__ q, long s0, int ny, int nx,
 // Two tile shapes: 16 columns x 1024 threads (one CTA per SM; a warp-wide global
 // access then covers 2 rows x 64/128 B instead of 4 rows x 32/64 B, which is what
 // the LSU data pipe is paid in) while the four planes fit 227 KB, else 8 x 512.
+#ifndef XC_FX_LEAN
+#define XC_FX_LEAN 0
+#endif
 #ifndef XC_FX_LUT            /* buckets of the LUT over Q.  The bisection that finishes the search is the most
                                 expensive source line of the kernel (9 % of its instructions, ncu source page); 4096
                                 buckets still fit the 16-column tile at ny = 721 (224 of 227 KB).  Not yet timed. */
@@ -420,8 +423,12 @@ __device__ __forceinline__ void fx_add64(uint32_t* lo, uint32_t* hi, int idx, lo
 {
     const uint32_t xl = (uint32_t)x, xh = (uint32_t)((unsigned long long)x >> 32);
     const uint32_t old = atomicAdd(lo + idx, xl);
+#if XC_FX_LEAN               /* carry from a 64-bit add (IADD3 + carry-out) instead of a comparison; prepared, not yet timed */
+    atomicAdd(hi + idx, xh + (uint32_t)(((unsigned long long)old + xl) >> 32));
+#else
     const uint32_t carry = (uint32_t)((old + xl) < xl);
     atomicAdd(hi + idx, xh + carry);
+#endif
 }
 
 // Per-slice preparation (one CTA per slice): the fixed-point scales from the
