@@ -1,5 +1,5 @@
 """
-Property tests (hypothesis) of the oracle itself -- CPU only.  They guard the
+Property tests (hypothesis, derandomized: the same examples on every run) of the oracle itself -- CPU only.  They guard the
 restatement against slips that the fixed-size tests could miss: random shapes,
 NaN cells, ties with the levels, both directions and both comparison senses.
 """
@@ -19,7 +19,7 @@ def _field(seed, ny, nx, nan_frac):
     return q, dA
 
 
-@settings(max_examples=40, deadline=None)
+@settings(max_examples=40, deadline=None, derandomize=True)
 @given(seed=st.integers(0, 10**6), ny=st.integers(4, 24), nx=st.integers(3, 30), N=st.integers(2, 40),
        increase=st.booleans(), lt=st.booleans(), nan_frac=st.sampled_from([0.0, 0.1]))
 def test_hist_cdf_invariants(seed, ny, nx, N, increase, lt, nan_frac):
@@ -42,7 +42,7 @@ def test_hist_cdf_invariants(seed, ny, nx, N, increase, lt, nan_frac):
     assert np.abs(a - s).max() <= slack
 
 
-@settings(max_examples=25, deadline=None)
+@settings(max_examples=25, deadline=None, derandomize=True)
 @given(seed=st.integers(0, 10**6), ny=st.integers(5, 40), nx=st.integers(2, 12),
        increase=st.booleans(), part=st.sampled_from(["all", "upper", "lower"]), ties=st.booleans())
 def test_lwa_reformulation_equals_reference_loop(seed, ny, nx, increase, part, ties):
@@ -58,12 +58,16 @@ def test_lwa_reformulation_equals_reference_loop(seed, ny, nx, increase, part, t
     brute = O.cal_local_wave_activity(q[None], Q, dA, coord, increase, part)
     fast = O.cal_local_wave_activity_fast(q[None], Q, dA, coord, increase, part)
     scale = max(np.abs(brute).max(), 1e-300)
-    assert np.abs(brute - fast).max() <= 1e-11 * scale
+    # the reformulation evaluates V_j - Q_j S_j: where a part is (almost) empty the field is ~0 and what is
+    # left is the rounding of the two sums, bounded by the size of their terms, not by the field maximum
+    ww = (dA / np.nanmax(dA)).astype(np.float64) * dA
+    floor = 8 * ny * np.finfo(np.float64).eps * np.nanmax(ww) * max(np.nanmax(np.abs(q)), np.abs(Q).max())
+    assert np.abs(brute - fast).max() <= 1e-11 * scale + floor
     if part == "all":
         assert (brute >= -1e-12 * scale).all() if increase else (brute <= 1e-12 * scale).all()
 
 
-@settings(max_examples=30, deadline=None)
+@settings(max_examples=30, deadline=None, derandomize=True)
 @given(seed=st.integers(0, 10**6), n=st.integers(2, 30), dtype=st.sampled_from([np.float32, np.float64]),
        time_branch=st.booleans(), decreasing=st.booleans())
 def test_hist_edges_structure(seed, n, dtype, time_branch, decreasing):
