@@ -253,8 +253,12 @@ def test_gather_contour_space_gloo_world2(tmp_path):
         "out = gather_contour_space({'area': full[lo:hi].clone()}, S)\n"
         "assert torch.equal(out['area'], full), out\n"
         "dist.barrier(); print('OK', r)\n" % ROOT)
+    import socket
+    with socket.socket() as sk:                               # a port that is free right now
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-           "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)]
+           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert res.returncode == 0, res.stdout + res.stderr
     assert res.stdout.count("OK") == 2
