@@ -5,10 +5,11 @@
 #   lean   -DXC_HKX_LEAN=1   k_hist_keff: funnel-shift decomposition, out-of-line truncation, 64-bit-add carries,
 #                            no division in the cell loop (hkx_add is 55 % of the kernel's instructions)
 #   fxlean -DXC_FX_LEAN=1    k_lwa_fx: carries of the 64-bit atomic adds from 64-bit integer adds
-#   all    all of them together
+#   own8   -DXC_FX_OWN=1 -DXC_FX_TC8=1   the own-deposit kernel on 8-column tiles, two CTAs per SM
+#   all    own + lut4k + lean + fxlean together
 #
 #   1. on the CPU (build container):
-#        python scripts/build_variants.py own:XC_FX_OWN=1 lut4k:XC_FX_LUT=4096 lean:XC_HKX_LEAN=1 fxlean:XC_FX_LEAN=1 \
+#        python scripts/build_variants.py own:XC_FX_OWN=1 lut4k:XC_FX_LUT=4096 lean:XC_HKX_LEAN=1 fxlean:XC_FX_LEAN=1 own8:XC_FX_OWN=1,XC_FX_TC8=1 \
 #               all:XC_FX_OWN=1,XC_FX_LUT=4096,XC_HKX_LEAN=1,XC_FX_LEAN=1
 #   2. on the GPU:   gpurun --timeout 600 -- 'bash scripts/ab_round2.sh'
 #
@@ -17,7 +18,7 @@
 # build on the benchmark field, a smooth one and a quantised one.
 mkdir -p gpurun_out
 D=$PWD/xcontour_b200
-( for v in own lut4k lean fxlean all; do
+( for v in own lut4k lean fxlean own8 all; do
     echo "== parity, variant $v"
     XCB200_LIB=$D/libxcb200_$v.so timeout 300 python -m pytest tests -m gpu -x -q \
         -k "lwa or lape or fused or workflow or reference_fixtures or full_size or cdf or hist or keff or accumulators or smoke" 2>&1 | tail -2
@@ -25,5 +26,5 @@ D=$PWD/xcontour_b200
   for env in "" "XC_NOISE=0" "XC_QUANT=8"; do
     echo "== field: ${env:-benchmark}"
     env $env python scripts/time_stages.py 32 32
-    for v in own lut4k lean fxlean all; do env $env XCB200_LIB=$D/libxcb200_$v.so python scripts/time_stages.py 32 32; done
+    for v in own lut4k lean fxlean own8 all; do env $env XCB200_LIB=$D/libxcb200_$v.so python scripts/time_stages.py 32 32; done
   done ) 2>&1 | grep -v Warning | tee gpurun_out/r2_ab.txt

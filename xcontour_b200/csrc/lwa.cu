@@ -1059,7 +1059,12 @@ int xc::lwa_impl(const void* q, int q_dtype, long S, int n_eq, int n_x, const do
     const bool match = lwa_use_match();
     const int qbytes = q_dtype == XC_F32 ? 4 : 8;
     const int tc = (n_eq < 65535) ? lwa_pick_tc(n_eq, qbytes, !match) : 0;
-    const int fx_tc = lwa_fx_layout(n_eq, 16).total <= 227 * 1024 ? 16 : 8;
+#ifndef XC_FX_TC8            /* 1: always the 8-column / 512-thread tile (two CTAs per SM overlap each other's barriers);
+                                with XC_FX_OWN the walk has no global loads left, which is what made 16 columns pay.
+                                A/B switch, not yet timed. */
+#define XC_FX_TC8 0
+#endif
+    const int fx_tc = (!XC_FX_TC8 && lwa_fx_layout(n_eq, 16).total <= 227 * 1024) ? 16 : 8;
     const LwaFxSmem FL = lwa_fx_layout(n_eq, fx_tc);
     const bool fx = (variant == 1) && lwa_use_fx() && scratch && n_eq < 65535 && FL.total <= 227 * 1024;
     const bool fast = fx || ((variant == 1) && tc >= 1 && (size_t)tc * (n_eq + 2) * 16 >= (size_t)(LWA_LUT + 1) * 2);
