@@ -380,6 +380,12 @@ k_lwa_fast(const QT* __restrict__ q, long s0, int ny, int nx,
 #ifndef XC_FX_LEAN
 #define XC_FX_LEAN 0
 #endif
+#ifndef XC_FX_PAIR           /* 1: the lo and hi word of an accumulator sit next to each other ([slot][column][lo,hi]), so
+                                the two prefix passes read one LDS.64 per accumulator and row instead of two LDS.32 and
+                                need no recombination.  A/B switch, not yet timed; the default path is textually
+                                untouched (every use is an #if / #else around the original statement). */
+#define XC_FX_PAIR 0
+#endif
 #ifndef XC_FX_LUT            /* buckets of the LUT over Q.  The bisection that finishes the search is the most
                                 expensive source line of the kernel (9 % of its instructions, ncu source page); 4096
                                 buckets still fit the 16-column tile at ny = 721 (224 of 227 KB).  Not yet timed. */
@@ -574,7 +580,11 @@ k_lwa_fx(const QT* __restrict__ q, long s0, long sbase, int ny, int nx,
     const int r0 = (int)(((long)seg * ny) / FX_SEG), r1 = (int)(((long)(seg + 1) * ny) / FX_SEG);
     const QT* qc = q + (s * (long)ny + r0) * nx + i;
     const double* wc = ww + (long)r0 * nx + i;
+#if XC_FX_PAIR
+    uint32_t* fcol = far + 2 * c;                              // S: fcol[t * 2 FX_TC + {0, 1}], V: 2 * plane further on
+#else
     uint32_t* fcol = far + c;                                  // word (slot t, plane k) = fcol[t * FX_TC + k * plane]
+#endif
 
     // ---- scatter: one deposit of -X at the far end of each cell's range ----
     long long ownS = 0, ownV = 0;
@@ -616,19 +626,31 @@ k_lwa_fx(const QT* __restrict__ q, long s0, long sbase, int ny, int nx,
 #if XC_FX_OWN
                 if (target == jp + 1) continue;                  // inactive: nothing to deposit
                 {
+#if XC_FX_PAIR
+                    uint32_t* so = fcol + (jp + 1) * 2 * FX_TC;  // +X at the own slot
+                    fx_add64(so, so + 1, 0, -NS);
+                    fx_add64(so + 2 * plane, so + 2 * plane + 1, 0, -NV);
+#else
                     uint32_t* so = fcol + (jp + 1) * FX_TC;      // +X at the own slot
                     fx_add64(so, so + plane, 0, -NS);
                     fx_add64(so + 2 * plane, so + 3 * plane, 0, -NV);
+#endif
                 }
 #else
                 ownS -= NS; ownV -= NV;
 #endif
+#if XC_FX_PAIR
+                uint32_t* slot = fcol + target * 2 * FX_TC;
+                fx_add64(slot, slot + 1, 0, NS);
+                fx_add64(slot + 2 * plane, slot + 2 * plane + 1, 0, NV);
+#else
                 uint32_t* slot = fcol + target * FX_TC;
 #if XC_FX_EXP == 1
                 ownS += (long long)(slot - far);                 // keeps the search alive without touching shared memory
 #else
                 fx_add64(slot, slot + plane, 0, NS);
                 fx_add64(slot + 2 * plane, slot + 3 * plane, 0, NV);
+#endif
 #endif
             }
         }
@@ -638,10 +660,18 @@ k_lwa_fx(const QT* __restrict__ q, long s0, long sbase, int ny, int nx,
     // ---- prefix down the columns: segment totals, block scan, final walk ----
     {
         unsigned long long aSl = 0, aVl = 0; long long aSh = 0, aVh = 0;
+#if XC_FX_PAIR
+        const uint32_t* sl = fcol + r0 * 2 * FX_TC;
+        for (int j = r0; j < r1; ++j, sl += 2 * FX_TC) {          // sums modulo 2^64
+            const uint2 a = *reinterpret_cast<const uint2*>(sl), b = *reinterpret_cast<const uint2*>(sl + 2 * plane);
+            aSl += ((unsigned long long)a.y << 32) | a.x; aVl += ((unsigned long long)b.y << 32) | b.x;
+        }
+#else
         const uint32_t* sl = fcol + r0 * FX_TC;
         for (int j = r0; j < r1; ++j, sl += FX_TC) {
             aSl += sl[0]; aSh += (int32_t)sl[plane]; aVl += sl[2 * plane]; aVh += (int32_t)sl[3 * plane];
         }
+#endif
         tot[c * FX_TOTP + seg] = (long long)aSl + (aSh << 32) + ownS;
         tot[(FX_TC + c) * FX_TOTP + seg] = (long long)aVl + (aVh << 32) + ownV;
     }
@@ -663,10 +693,20 @@ k_lwa_fx(const QT* __restrict__ q, long s0, long sbase, int ny, int nx,
         const QT* qp = qc; const double* wp = wc;
         const uint32_t* sl = fcol + r0 * FX_TC;
         const double* Qj = Qs + r0;
+#if XC_FX_PAIR && !XC_FX_OWN
+#error "XC_FX_PAIR is implemented for the XC_FX_OWN walk only"
+#endif
 #if XC_FX_OWN
         for (int j = r0; j < r1; ++j) {                          // every deposit is in the planes: a plain inclusive prefix
+#if XC_FX_PAIR
+            const uint32_t* sp = fcol + j * 2 * FX_TC;
+            const uint2 a = *reinterpret_cast<const uint2*>(sp), b = *reinterpret_cast<const uint2*>(sp + 2 * plane);
+            RS += (long long)(((unsigned long long)a.y << 32) | a.x);
+            RV += (long long)(((unsigned long long)b.y << 32) | b.x);
+#else
             RS += (long long)(((unsigned long long)sl[plane] << 32) | sl[0]);
             RV += (long long)(((unsigned long long)sl[3 * plane] << 32) | sl[2 * plane]);
+#endif
             const double Sj = __dmul_rn(fx_to_double(RS), fiS), Vj = __dmul_rn(fx_to_double(RV), fiV);
             *op = sg * (Vj - (*Qj - fc) * Sj);
             op += nx; sl += FX_TC; ++Qj;
