@@ -30,23 +30,42 @@ def _module(name, **attrs):
     return m
 
 
+BACKEND = None        # "refshim" or "xarray <version> + xhistogram <version>" once install() has run
+
+
+def _importable(name):
+    try:
+        importlib.import_module(name)
+        return True
+    except Exception:
+        return False
+
+
 def install():
-    """Register the stand-ins under the names the reference imports."""
+    """Make `import xarray`, `from xhistogram.xarray import histogram`, `from skimage import measure` and
+    `from xgcm import Grid` work.  When the REAL xarray and xhistogram are both installed they are used (the
+    golden vectors then come from the true stack); otherwise both are replaced by the stand-ins -- never a mix."""
+    global BACKEND
+
     def unavailable(*a, **k):
         raise NotImplementedError("outside the hot path: not provided by oracle/refshim")
-    if "xarray" not in sys.modules:
+    if _importable("xarray") and _importable("xhistogram.xarray"):
+        import xarray
+        import xhistogram
+        BACKEND = "xarray %s + xhistogram %s" % (xarray.__version__, getattr(xhistogram, "__version__", "?"))
+    else:
         sys.modules["xarray"] = xarray_shim
-    if "xhistogram" not in sys.modules:
         xh = _module("xhistogram")
         xh.xarray = _module("xhistogram.xarray", histogram=xhistogram_shim.histogram)
         sys.modules["xhistogram"] = xh
         sys.modules["xhistogram.xarray"] = xh.xarray
-    if "skimage" not in sys.modules:
+        BACKEND = "refshim"
+    if not _importable("skimage.measure"):
         sk = _module("skimage")
         sk.measure = _module("skimage.measure", find_contours=unavailable)
         sys.modules["skimage"] = sk
         sys.modules["skimage.measure"] = sk.measure
-    if "xgcm" not in sys.modules:
+    if not _importable("xgcm.autogenerate"):
         xg = _module("xgcm", Grid=unavailable)
         xg.autogenerate = _module("xgcm.autogenerate", generate_grid_ds=unavailable)
         sys.modules["xgcm"] = xg

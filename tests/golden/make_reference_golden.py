@@ -231,6 +231,7 @@ def generate(from_committed=False):
         d.update({"out/" + k: np.asarray(v) for k, v in out.items()})
         d["meta/numpy"] = np.array(np.__version__)
         d["meta/scalar_rules"] = np.array(regime)
+        d["meta/array_backend"] = np.array(refshim.BACKEND)
         packed[name] = d
     return packed
 
