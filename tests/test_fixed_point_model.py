@@ -162,3 +162,31 @@ def test_lean_term_decomposition_equals_the_default(tmp_path):
     subprocess.check_call(["g++", "-O2", "-o", exe, os.path.join(root, "tests", "host", "hkx_decompose_test.cpp")])
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and " 0 mismatches" in r.stdout, r.stdout[-500:]
+
+
+def test_row_count_area_model():
+    """Model of the prepared -DXC_HKX_ROWCNT=1 build: on a grid whose dA is constant along a row the area of
+    a bin is sum_rows dA[row] * (cells of that row in the bin); the counts are packed two per 32-bit word
+    (u16 halves, one ATOMS.ADD per cell) and every product dA * count is exact in fp64."""
+    rng = np.random.default_rng(11)
+    ny, nx, N = 37, 1440, 361
+    dA_row = (np.cos(np.deg2rad(np.linspace(-89.9, 89.9, ny))) * 7.7e8).astype(np.float32)
+    bins = rng.integers(-1, N, size=(ny, nx))                        # -1: outside / NaN
+    bins[5, :] = 17                                                  # a whole row in one bin: the largest count
+    words = np.zeros((ny, (N + 1) >> 1), dtype=np.uint32)
+    for j in range(ny):
+        for b in bins[j][bins[j] >= 0]:
+            words[j, b >> 1] += np.uint32(1) << np.uint32((b & 1) << 4)
+    assert ((words & 0xffff) <= nx).all() and ((words >> 16) <= nx).all()      # no carry between the halves
+    area = np.zeros(N)
+    for n in range(N):
+        t = 0.0
+        for j in range(ny):
+            cn = int(words[j, n >> 1] >> ((n & 1) << 4)) & 0xffff
+            if cn:
+                assert float(dA_row[j]) * cn == float(np.float64(dA_row[j]) * np.float64(cn))    # 24 + 11 bits: exact
+                t += float(dA_row[j]) * cn
+        area[n] = t
+    ref = np.bincount(bins[bins >= 0], weights=np.broadcast_to(dA_row[:, None], bins.shape)[bins >= 0].astype(np.float64),
+                      minlength=N)
+    assert np.abs(area - ref).max() <= 1e-14 * ref.max()

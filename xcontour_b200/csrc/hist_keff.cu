@@ -144,6 +144,13 @@ constexpr int HKX_MARGIN = 12;           // windows start this many bits below t
                                 weights are computed but nothing is accumulated (scripts/lwa_split.sh) */
 #define XC_HKX_EXP 0
 #endif
+#ifndef XC_HKX_ROWCNT        /* 1: the AREA of every cell whose dA equals the first dA of its row (all of them on a lat-lon
+                                grid) is accumulated as an exact integer cell count per (row, bin) -- one ATOMS.ADD --
+                                and multiplied by that dA once per row at the end; other cells keep the windowed add.
+                                hkx_add is 55 % of the kernel's instructions and the area is half of it.  A/B switch,
+                                not yet timed (scripts/ab_round2.sh). */
+#define XC_HKX_ROWCNT 0
+#endif
 #ifndef XC_HKX_LEAN          /* 1: same sums from fewer instructions -- 32-bit funnel shifts instead of 64-bit variable
                                 shifts (hkx_decompose.cuh, checked on the CPU against the default statement), the
                                 below-anchor truncation out of line, carries from 64-bit adds, no division in the cell
@@ -245,11 +252,19 @@ __device__ __forceinline__ void hkx_scatter(uint32_t* accA, uint32_t* accG, doub
             const int gn = __shfl_sync(XC_FULL, nxt, src);
             if (nxt >= 0) { w0 += g0; w1 += g1; nxt = gn; }
         }
+#if XC_HKX_ROWCNT
+        if (leader) hkx_add(accG, escG, N, bin, eG, w1);         // the area went to the row counts
+#else
         if (leader) { hkx_add(accA, escA, N, bin, eA, w0); hkx_add(accG, escG, N, bin, eG, w1); }
+#endif
         return;
     }
 #endif
+#if XC_HKX_ROWCNT
+    if (bin >= 0) hkx_add(accG, escG, N, bin, eG, w1);
+#else
     if (bin >= 0) { hkx_add(accA, escA, N, bin, eA, w0); hkx_add(accG, escG, N, bin, eG, w1); }
+#endif
 }
 
 // grid = (C, nslices), block = 16 warps, 2 CTAs per SM.
@@ -264,6 +279,10 @@ k_hist_keff(const HistKeffParams p)
     double*   esc = reinterpret_cast<double*>(H);                     //  FX: [2][N] side table, then
     uint32_t* acc = reinterpret_cast<uint32_t*>(esc + 2 * N);         //      [2][HKX_NW][N][3] window accumulators
     const size_t accn = (size_t)HKX_NW * N * 3;
+#if XC_HKX_ROWCNT
+    uint32_t* cnt = acc + 2 * accn;                                   //      [rows of this CTA][(N+1)/2] packed u16 cell counts
+    const int CW = (N + 1) >> 1, cnt_rows = p.per / p.nx + 2;
+#endif
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long s = p.s0 + blockIdx.y;
     const int c = blockIdx.x, C = gridDim.x;
@@ -273,6 +292,9 @@ k_hist_keff(const HistKeffParams p)
     if (FX) {
         for (int i = tid; i < 2 * N; i += blockDim.x) esc[i] = 0.0;
         for (int i = tid; i < (int)(2 * accn); i += blockDim.x) acc[i] = 0u;
+#if XC_HKX_ROWCNT
+        for (int i = tid; i < cnt_rows * CW; i += blockDim.x) cnt[i] = 0u;
+#endif
     } else {
         for (int i = tid; i < HK_WARPS * N; i += blockDim.x) H[i] = make_double2(0.0, 0.0);
     }
@@ -365,6 +387,16 @@ k_hist_keff(const HistKeffParams p)
                 eA = (mA == 0x7fffffff ? 1023 - 72 : mA) - HKX_MARGIN;
                 eG = (mG == 0x7fffffff ? 1023 - 72 : mG) - HKX_MARGIN;
             }
+#if XC_HKX_ROWCNT
+            if (ok) {                                       // area: integer counts where dA is the row's own value
+                const float aref = __ldg(p.dA + (long)j * nx);
+                uint32_t* crow = cnt + (size_t)(j - beg / nx) * CW;
+                if (b0 >= 0) { if (a4.x == aref) atomicAdd(crow + (b0 >> 1), 1u << ((b0 & 1) << 4)); else hkx_add(acc, esc, N, b0, eA, a0); }
+                if (b1 >= 0) { if (a4.y == aref) atomicAdd(crow + (b1 >> 1), 1u << ((b1 & 1) << 4)); else hkx_add(acc, esc, N, b1, eA, a1); }
+                if (b2 >= 0) { if (a4.z == aref) atomicAdd(crow + (b2 >> 1), 1u << ((b2 & 1) << 4)); else hkx_add(acc, esc, N, b2, eA, a2); }
+                if (b3 >= 0) { if (a4.w == aref) atomicAdd(crow + (b3 >> 1), 1u << ((b3 & 1) << 4)); else hkx_add(acc, esc, N, b3, eA, a3); }
+            }
+#endif
             // smooth stretch of the field (neighbouring lanes in the same bin): combine in registers first
             const int nb = __shfl_down_sync(XC_FULL, b0, 1);
             const bool crowded = __popc(__ballot_sync(XC_FULL, b0 >= 0 && b0 == nb)) >= XC_HKX_CROWD;
@@ -421,6 +453,15 @@ k_hist_keff(const HistKeffParams p)
 #pragma unroll
             for (int w = 0; w < HKX_NW; ++w)                     // smallest window first
                 t += hkx_window(a + (size_t)w * N * 3, eb + w * HKX_WBITS - 1075);
+#if XC_HKX_ROWCNT
+            if (k == 0 && end > beg) {                           // + dA[row] * cells of that row in the bin, row by row (exact products)
+                const int jf = beg / nx, nrows = (end - 1) / nx - jf + 1;
+                for (int r = 0; r < nrows; ++r) {
+                    const uint32_t cn = (cnt[(size_t)r * CW + (n >> 1)] >> ((n & 1) << 4)) & 0xffffu;
+                    if (cn) t += (double)__ldg(p.dA + (long)(jf + r) * nx) * (double)cn;
+                }
+            }
+#endif
             out[idx] = t + esc[idx];
         }
         return;
@@ -458,7 +499,14 @@ int xc::hist_keff_try(const void* q, int q_dtype, long S, long P, const double* 
     const size_t smem_fx = (size_t)((N + 2) & ~1) * 8 + (size_t)2 * N * 8 + (size_t)2 * HKX_NW * N * 3 * 4;
     const size_t smem_rmw = (size_t)((N + 2) & ~1) * 8 + (size_t)HK_WARPS * N * 16 + (size_t)HK_WARPS * ((N + 15) & ~15);
     const long per = (((P + C - 1) / C) + 3) & ~3L;
-    const bool fx = !(fxe && fxe[0] == '0') && smem_fx <= 113 * 1024 && per <= (1L << 18);   // <= 2^18 terms of < 2^77 per bin and CTA: 95 bits
+#if XC_HKX_ROWCNT
+    const size_t smem_cnt = (size_t)(per / st->nx + 2) * ((N + 1) >> 1) * 4;
+    const size_t smem_fx_all = smem_fx + smem_cnt;
+    const bool fx = !(fxe && fxe[0] == '0') && smem_fx_all <= 113 * 1024 && per <= (1L << 18) && st->nx <= 65535;
+#define smem_fx smem_fx_all
+#else
+    const bool fx = !(fxe && fxe[0] == '0') && smem_fx <= 113 * 1024 && per <= (1L << 18);
+#endif   // <= 2^18 terms of < 2^77 per bin and CTA: 95 bits
     const size_t smem = fx ? smem_fx : smem_rmw;
     if (smem > 100 * 1024 && !fx) return 1;           // two CTAs per SM
     HistKeffParams p;
