@@ -46,6 +46,13 @@ extern "C" {
 
 #define XC_MAX_INTEGRANDS 3
 
+/* ghost cells of the |grad q|^2 stencil (numpy.pad vocabulary in brackets); the reference's callers choose
+ * them in xinvert.FiniteDiff(BCs=...) / GeoApps (tests/test_Keff_ocean.py:26-32, tests/test_clength.py:39-45) */
+#define XC_BC_PERIODIC 0 /* wrap around                              ['wrap']     */
+#define XC_BC_EXTEND   1 /* ghost = value of the edge cell           ['edge']     */
+#define XC_BC_REFLECT  2 /* mirror about the edge point, q[-1]=q[1]  ['reflect']  */
+#define XC_BC_FILL     3 /* ghost = fill_value                       ['constant'] */
+
 const char* xc_last_error(void);
 int         xc_abi_version(void);
 
@@ -219,7 +226,7 @@ typedef struct xc_keff_lwa_args {
     int           ctr_dtype;  /* Contour2D(dtype=...) : XC_F32 default */
     const void*   dA;         int dA_dtype;
     const void*   grdS;       int grdS_dtype;       /* nullable */
-    const double* lat_rad;    double dlambda;       /* stencil metrics (grdS == NULL) */
+    const double* lat_rad;    double dlambda;       /* lat-lon stencil metrics (grdS == NULL and cx == NULL) */
     const double* table;      const double* table_coord; int n_table; /* A(Yeq), ascending coord */
     const double* eq_coord;   /* [n_y] coordinate values Q is interpolated to */
     const double* ww;         /* [n_y][n_x] from xc_lwa_weights */
@@ -233,6 +240,19 @@ typedef struct xc_keff_lwa_args {
      * non-NULL the call synchronises the stream before returning.  Stages:
      * 0 min/max+levels, 1 edges, 2 binning+scan, 3 contour-space epilogue, 4 LWA. */
     float* stage_ms;
+    /* ---- ABI version 2 ---- */
+    /* general stencil (grdS == NULL): row metrics [n_y] fp64 with dq/dx = (q[i+1]-q[i-1])*cx[j] and
+     * dq/dy = (q[j+1]-q[j-1])*cy[j] (lat-lon, Cartesian, X-Z ...), ghost cells by bcx / bcy (XC_BC_*).
+     * cx == NULL: lat-lon metrics from lat_rad / dlambda, periodic in x, edge value in y. */
+    const double* cx;         const double* cy;
+    int           bcx, bcy;   double fill_value;
+    /* optional hints that select the fast kernels (results are the same without them):
+     * dA_row [n_y] fp64: the cell area of every row when dA is constant along x (as on every regular
+     *   lat-lon / Cartesian / X-Z grid); uniform_dA: all rows have the same area; any_degenerate: some row has
+     *   cx^2 > 2^30 cy^2 (a pole row) -- reserves the accumulator of such rows.
+     * ww_row [n_y] fp64: ww of every row when the LWA weights are constant along x. */
+    const double* dA_row;     int uniform_dA;  int any_degenerate;
+    const double* ww_row;
 } xc_keff_lwa_args;
 #define XC_N_STAGES 5
 

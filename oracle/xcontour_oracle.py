@@ -520,6 +520,51 @@ def squared_gradient_latlon(q, lat_deg, lon_deg):
     return dqdx * dqdx + dqdy * dqdy
 
 
+BOUNDARY_PAD = {"periodic": "wrap", "extend": "edge", "reflect": "reflect", "fill": "constant"}
+
+
+def row_metrics_latlon(lat_deg, lon_deg):
+    """(cx, cy) of squared_gradient_latlon, see there."""
+    phi = np.deg2rad(np.asarray(lat_deg, dtype=np.float64))
+    lam = np.deg2rad(np.asarray(lon_deg, dtype=np.float64))
+    ny = phi.shape[0]
+    jm = np.maximum(np.arange(ny) - 1, 0)
+    jp = np.minimum(np.arange(ny) + 1, ny - 1)
+    with np.errstate(divide="ignore"):
+        return 1.0 / ((2.0 * (lam[1] - lam[0])) * (Rearth * np.cos(phi))), 1.0 / ((phi[jp] - phi[jm]) * Rearth)
+
+
+def row_metrics_cartesian(y, x):
+    """cx = 1/(2 dx) (uniform x), cy[j] = 1/(y[j+1]-y[j-1]), the interior spacing continued at both ends."""
+    y = np.asarray(y, dtype=np.float64)
+    x = np.asarray(x, dtype=np.float64)
+    d = np.empty(y.shape[0])
+    d[1:-1] = y[2:] - y[:-2]
+    d[0] = 2.0 * (y[1] - y[0])
+    d[-1] = 2.0 * (y[-1] - y[-2])
+    return np.full(y.shape[0], 1.0 / (2.0 * (x[1] - x[0]))), 1.0 / d
+
+
+def squared_gradient(q, cx, cy, bcx="periodic", bcy="extend", fill=0.0):
+    """|grad q|^2 by centred differences with one layer of ghost cells:
+        dq/dx = (q[j,i+1] - q[j,i-1]) * cx[j],   dq/dy = (q[j+1,i] - q[j-1,i]) * cy[j]
+    ghost cells by numpy.pad: 'periodic' -> wrap, 'extend' -> edge, 'reflect' -> reflect, 'fill' -> constant.
+    The reference takes this field from xinvert.FiniteDiff(BCs=...) / GeoApps (tests/test_Keff_ocean.py:26-32,
+    tests/test_clength.py:39-45), whose sources are not under /root/reference: parity UNPINNED, the definition
+    is ours; squared_gradient_latlon is the (periodic, extend) case with lat-lon metrics."""
+    q = np.asarray(q, dtype=np.float64)
+
+    def pad(axis, mode):
+        pw = [(0, 0)] * q.ndim
+        pw[axis] = (1, 1)
+        kw = {"constant_values": float(np.float32(fill))} if mode == "fill" else {}
+        return np.pad(q, pw, mode=BOUNDARY_PAD[mode], **kw)
+    qx, qy = pad(-1, bcx), pad(-2, bcy)
+    dqdx = (qx[..., 2:] - qx[..., :-2]) * np.asarray(cx)[:, None]
+    dqdy = (qy[..., 2:, :] - qy[..., :-2, :]) * np.asarray(cy)[:, None]
+    return dqdx * dqdx + dqdy * dqdy
+
+
 # --------------------------------------------------------------------------
 # raw reader for the one data file that is present (SURVEY.md §8c)
 # --------------------------------------------------------------------------

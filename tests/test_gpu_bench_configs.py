@@ -1,0 +1,313 @@
+"""
+GPU parity at the sizes bench.py is quoted on (-m gpu): BASELINE.json config 4
+(721x1440, 361 contours, Keff + LWA) and config 5 (4096x8192, 2048 contours, Keff
+part) against the NumPy oracle on the same seeded inputs, plus the callers around
+the fused batch (HostStreamer, torch / DLPack inputs of the drop-in class).
+
+Reference path being checked: xcontour/core.py:205-266 (levels), :412-460 +
+:1202-1325 (histogram / CDF), :463-488 (d/dA), :619-637 + :945-966 (Keff),
+:1050-1100 (Q), :696-799 (LWA).
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from conftest import synth_c4
+from oracle import xcontour_oracle as O
+from test_gpu_parity import _close, _oracle_keff_chain, relmax
+
+pytestmark = pytest.mark.gpu
+
+RTOL_INT = 1e-12      # integrals, relative to the array maximum (bar of north_star: 1e-10)
+RTOL_FIELD = 1e-12    # LWA, relative to the field maximum (bar: 1e-10)
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from xcontour_b200 import ops as _ops
+    _ops.require_cuda()
+    return _ops
+
+
+def dev(ops, a):
+    return ops.to_dev(np.ascontiguousarray(a))
+
+
+# ---------------------------------------------------------------- config 4
+@pytest.fixture(scope="module")
+def c4(ops):
+    """Two full-size slices through the fused batch (the call bench.py times)."""
+    from xcontour_b200.pipeline import KeffLwaPlan
+    lat, lon, q = synth_c4(2)
+    dA = O.latlon_cell_area(lat, lon).astype(np.float32)
+    plan = KeffLwaPlan(lat, lon, dA, 361, increase=True, lt=True)
+    qd = dev(ops, q)
+    out = plan.run(qd)
+    torch.cuda.synchronize()
+    return lat, lon, q, dA, plan, qd, out
+
+
+def test_c4_contour_space_matches_oracle_chain(ops, c4):
+    """Every contour-space result of both slices at 721x1440 / N = 361 against the oracle chain."""
+    lat, lon, q, dA, plan, qd, out = c4
+    grd = O.squared_gradient_latlon(q, lat, lon)
+    ref = _oracle_keff_chain(q, lat, lon, dA, grd, 361, True, True)
+    got = {k: v.cpu().numpy() for k, v in out.items() if k != "lwa"}
+    assert np.array_equal(got["ctr"].astype(np.float32), ref["ctr"])          # levels bit-exact
+    assert relmax(got["area"], ref["area"]) <= RTOL_INT
+    # |grad q|^2 dA: the polar rows put single terms 2^100 above the mid-latitude ones, so the CDF is held
+    # (i) to its own maximum and (ii) bin by bin (pdf) to each bin's own value
+    assert relmax(got["intgrdS"], ref["intgrdS"]) <= RTOL_INT
+    pdf_got = np.diff(got["intgrdS"], axis=1, prepend=0.0)
+    pdf_ref = np.diff(ref["intgrdS"], axis=1, prepend=0.0)
+    small = ref["intgrdS"] < 1e-3 * ref["intgrdS"].max(axis=1, keepdims=True)   # bins below the polar blow-up
+    assert small.sum() > 300
+    assert np.allclose(pdf_got[small], pdf_ref[small], rtol=1e-9, atol=1e-13 * np.abs(pdf_ref[small]).max())
+    _close(got["latEq"], ref["latEq"], 1e-11)
+    _close(got["Lmin"], ref["Lmin"], 1e-9)
+    _close(got["dqdA"], ref["dqdA"], 1e-10)
+    _close(got["dintSdA"], ref["dintSdA"], 1e-9)
+    _close(got["Leq2"], ref["Leq2"], 1e-8)
+    _close(got["nkeff"], ref["nkeff"], 1e-8)
+    Qref = O.interp_to_coords(lat.astype(np.float32), ref["latEq"], ref["ctr"])
+    _close(got["Qref"], Qref, 1e-11)
+
+
+def test_c4_bins_bit_exact_both_slices(ops, c4):
+    lat, lon, q, dA, plan, qd, out = c4
+    ctr = out["ctr"].cpu().numpy().astype(np.float32)
+    ee, dd = ops.hist_edges(out["ctr"].contiguous(), 0, True)
+    _, _, idx = ops.bin_accumulate(qd.reshape(2, -1), ee, dev(ops, dA.reshape(-1)), decreasing=dd, want_idx=True)
+    idx = idx.cpu().numpy()
+    for s in range(2):
+        e, _ = O.hist_edges(ctr[s], True)
+        assert np.array_equal(idx[s], O.digitize_bins(q[s].ravel(), e))
+
+
+def test_c4_lwa_rows_match_reference_loop(ops, c4):
+    """40 rows of each slice (both poles, their neighbours, an even spread) against the reference's own
+    j-loop (core.py:752-794) at full size."""
+    lat, lon, q, dA, plan, qd, out = c4
+    rows = sorted(set([0, 1, 2, 359, 360, 361, 718, 719, 720] + list(range(5, 721, 23))))
+    assert len(rows) >= 32
+    Q = out["Qref"].cpu().numpy()
+    lwa = out["lwa"].cpu().numpy()
+    ref = O.cal_local_wave_activity(q, Q, dA, lat, True, rows=rows)
+    for s in range(2):
+        for j in rows:
+            assert np.abs(lwa[s, j] - ref[s, j]).max() <= RTOL_FIELD * lwa[s].max(), (s, j)
+    assert lwa.min() >= -1e-12 * lwa.max()
+
+
+def test_c4_run_to_run_bit_identical(ops, c4):
+    """Integer accumulators: every output, LWA included, is bit-reproducible whatever the schedule."""
+    lat, lon, q, dA, plan, qd, out = c4
+    for _ in range(2):
+        out2 = plan.run(qd, out=plan.alloc_outputs(2))
+        torch.cuda.synchronize()
+        for k in out:
+            assert torch.equal(out2[k].nan_to_num(), out[k].nan_to_num()), k
+
+
+def test_c4_batch_split_does_not_change_results(ops, c4):
+    """sub_batch (slices per pass) and the position of a slice in the batch are invisible in the results."""
+    from xcontour_b200.pipeline import KeffLwaPlan
+    lat, lon, q, dA, plan, qd, out = c4
+    plan1 = KeffLwaPlan(lat, lon, dA, 361, increase=True, lt=True, sub_batch=1)
+    out1 = plan1.run(qd.flip(0).contiguous())
+    torch.cuda.synchronize()
+    for k in out:
+        assert torch.equal(out1[k].flip(0).nan_to_num(), out[k].nan_to_num()), k
+
+
+def test_host_streamer_equals_plan_run(ops):
+    """pipeline.HostStreamer (pinned host -> H2D -> fused batch -> D2H, buffers in flight): every host array it
+    hands to `consume` equals plan.run on the same slices, including a ragged last batch."""
+    from xcontour_b200.pipeline import HostStreamer, KeffLwaPlan
+    lat, lon, q = synth_c4(7, 181, 360)
+    dA = O.latlon_cell_area(lat, lon).astype(np.float32)
+    plan = KeffLwaPlan(lat, lon, dA, 91, increase=True, lt=True)
+    ref = {k: v.cpu() for k, v in plan.run(dev(ops, q)).items()}
+    torch.cuda.synchronize()
+    qh = torch.from_numpy(q).pin_memory()
+    for batch, nbuf in ((3, 2), (2, 3), (7, 2)):
+        hs = HostStreamer(plan, batch, nbuf=nbuf)
+        seen = []
+
+        def consume(s0, s1, host):
+            seen.append((s0, s1))
+            for k, v in host.items():
+                assert torch.equal(v.nan_to_num(), ref[k][s0:s1].nan_to_num()), (k, s0, s1)
+        hs.run(qh, consume=consume)
+        assert sorted(seen) == [(b, min(7, b + batch)) for b in range(0, 7, batch)]
+        assert hs.h2d_bytes == q.nbytes
+        assert hs.d2h_bytes == sum(v.numel() * v.element_size() for v in ref.values())
+
+
+class _DLPackOnly(object):
+    """An array that can ONLY be consumed through the DLPack protocol (no __array__, no torch type)."""
+
+    def __init__(self, t):
+        self._t = t
+        self.shape, self.ndim = tuple(t.shape), t.dim()
+
+    def __dlpack__(self, *a, **k):
+        return self._t.__dlpack__(*a, **k)
+
+    def __dlpack_device__(self):
+        return self._t.__dlpack_device__()
+
+
+def test_contour2d_accepts_torch_and_dlpack_tracers(ops, vort):
+    """north_star: 'exchanges buffers with torch via DLPack'.  The drop-in class takes a numpy array, a CUDA /
+    CPU torch.Tensor or any DLPack exporter as the tracer's values and returns the same numbers."""
+    import xcontour_b200 as xb
+    lat, lon, q = vort
+    q = q[::4, ::4].copy(); lat = lat[::4].copy(); lon = lon[::4].copy()
+    dA = O.latlon_cell_area(lat, lon).astype(np.float32)
+    coords = {"latitude": lat, "longitude": lon}
+    dAx = xb.DataArray(dA, dims=("latitude", "longitude"), coords=coords)
+
+    def chain(values):
+        tr = xb.DataArray(values, dims=("latitude", "longitude"), coords=coords, name="pv")
+        an = xb.Contour2D(tr, dAx, dims={"X": "longitude", "Y": "latitude"}, dimEq={"Y": "latitude"},
+                          increase=True, lt=True)
+        ctr = an.cal_contours(41)
+        area = an.cal_integral_within_contours_hist(ctr)
+        table = an.cal_area_eqCoord_table_hist(xb.DataArray(np.ones_like(dA), dims=("latitude", "longitude"), coords=coords))
+        latEq = table.lookup_coordinates(area)
+        Q = an.interp_to_coords(xb.DataArray(lat, dims=("latitude",), coords={"latitude": lat}), latEq, ctr)
+        lwa = an.cal_local_wave_activity(tr, Q)
+        return [np.asarray(x.values) for x in (ctr, area, latEq, Q, lwa)]
+
+    base = chain(q)
+    assert relmax(base[1], O.cal_integral_within_contours_hist(q[None], base[0], dA, True)[0]) <= RTOL_INT
+    for values in (torch.from_numpy(q), torch.from_numpy(q).cuda(), _DLPackOnly(torch.from_numpy(q).cuda()),
+                   _DLPackOnly(torch.from_numpy(q))):
+        got = chain(values)
+        for a, b in zip(got, base):
+            assert np.array_equal(a, b, equal_nan=True)
+
+
+# ---------------------------------------------------------------- config 5
+def _c5_field(S=1, ny=4096, nx=8192):
+    y = (np.arange(ny) + 0.5) / ny
+    x = (np.arange(nx) + 0.5) / nx
+    out = np.empty((S, ny, nx), np.float32)
+    for s in range(S):
+        rng = np.random.default_rng(4321 + s)
+        out[s] = (y[:, None] + 0.2 * np.sin(8 * np.pi * x)[None, :] * np.sin(4 * np.pi * y)[:, None]
+                  + 0.01 * rng.standard_normal((ny, nx))).astype(np.float32)
+    return y, x, out
+
+
+def test_c5_histogram_scan_stress_matches_oracle(ops):
+    """BASELINE config 5: 4096x8192 Cartesian tracer, 2048 contour levels, area + an fp32 integrand.
+    Levels and bin assignment bit-exact, both CDFs <= 1e-12 of their maximum."""
+    ny, nx, N = 4096, 8192, 2048
+    y, x, q = _c5_field(1, ny, nx)
+    rng = np.random.default_rng(99)
+    dA = np.full((ny, nx), 1.0 / (ny * nx))
+    g = rng.random((1, ny, nx)).astype(np.float32)
+    qd, dAd, gd = dev(ops, q.reshape(1, -1)), dev(ops, dA.reshape(-1)), dev(ops, g.reshape(1, -1))
+    lv, _ = ops.minmax_levels(qd, N, True, 0)
+    ctr = O.cal_contours(q, N, True)
+    assert np.array_equal(lv.cpu().numpy().astype(np.float32), ctr)
+    e, d = ops.hist_edges(lv, 0, True)
+    cdf, _, idx = ops.bin_accumulate(qd, e, dAd, acc_area=True, integrands=[gd], decreasing=d, want_idx=True)
+    eh, _ = O.hist_edges(ctr[0], True)
+    assert np.array_equal(idx.cpu().numpy()[0], O.digitize_bins(q[0].ravel(), eh))
+    ref_a = O.cal_integral_within_contours_hist(q, ctr, dA, True)
+    ref_g = O.cal_integral_within_contours_hist(q, ctr, dA, True, integrand=g)
+    c = cdf.cpu().numpy()
+    assert relmax(c[:, 0], ref_a) <= RTOL_INT
+    assert relmax(c[:, 1], ref_g) <= RTOL_INT
+
+
+# ---------------------------------------------------------------- general stencil (A9) through the row-march kernel
+def _plan_chain_reference(q, y, dA, grd, N, increase, lt):
+    ctr = O.cal_contours(q, N, increase)
+    area = O.cal_integral_within_contours_hist(q, ctr, dA, lt)
+    intg = O.cal_integral_within_contours_hist(q, ctr, dA, lt, integrand=grd)
+    return ctr, area, intg
+
+
+@pytest.mark.parametrize("bcx,bcy", [("periodic", "extend"), ("extend", "reflect"), ("fill", "fill"),
+                                     ("reflect", "periodic")])
+def test_cartesian_stencil_boundaries_in_flight(ops, bcx, bcy):
+    """|grad q|^2 with every ghost-cell rule on an X-Z / Cartesian plane (non-uniform, DESCENDING row
+    coordinate, row-dependent cell areas, NaN cells = topography), computed inside the binning pass,
+    against the oracle's np.pad statement (callers' BCs: tests/test_Keff_ocean.py:26-32,
+    tests/test_clength.py:39-45)."""
+    from xcontour_b200.pipeline import KeffLwaPlan
+    from xcontour_b200.utils import row_metrics_cartesian
+    rng = np.random.default_rng(11)
+    ny, nx, S, N = 83, 152, 3, 47
+    z = -np.cumsum(1.0 + rng.random(ny))                       # descending, non-uniform
+    x = np.arange(nx) * 250.0
+    q = (np.linspace(20, 2, ny)[None, :, None] + 0.6 * np.sin(2 * np.pi * x / x[-1] * 3 + np.arange(S)[:, None, None])
+         + 0.1 * rng.standard_normal((S, ny, nx))).astype(np.float32)
+    q[0, 60:, 40:70] = np.nan                                   # topography
+    q[2, 0, 0] = np.nan
+    dA = np.repeat((np.abs(np.gradient(z)) * 250.0)[:, None], nx, axis=1)          # fp64, row-constant
+    cx, cy = row_metrics_cartesian(z, x)
+    assert np.array_equal(np.stack([cx, cy]), np.stack(O.row_metrics_cartesian(z, x)))
+    grd = O.squared_gradient(q, cx, cy, bcx, bcy, fill=1.5)
+    for increase, lt in ((False, True), (True, False)):
+        plan = KeffLwaPlan(z, x, dA, N, increase=increase, lt=lt, metrics=(cx, cy), boundary=(bcx, bcy), fill_value=1.5)
+        out = plan.run(dev(ops, q))
+        torch.cuda.synchronize()
+        ctr, area, intg = _plan_chain_reference(q, z, dA, np.nan_to_num(grd, nan=0.0), N, increase, lt)
+        assert np.array_equal(out["ctr"].cpu().numpy().astype(np.float32), ctr)
+        assert relmax(out["area"].cpu().numpy(), area) <= RTOL_INT
+        assert relmax(out["intgrdS"].cpu().numpy(), intg) <= RTOL_INT
+        out2 = plan.run(dev(ops, q))
+        torch.cuda.synchronize()
+        assert torch.equal(out2["intgrdS"], out["intgrdS"]) and torch.equal(out2["area"], out["area"])
+
+
+def test_row_march_kernel_equals_general_kernel(ops, monkeypatch):
+    """The row-march binning kernel (bin_rows.cu) against the general fp64 read-modify-write kernel (hist.cu) on
+    the same call: bin-by-bin agreement of the pdfs to 1e-13 of each bin's own value, incl. the pole rows."""
+    from xcontour_b200.pipeline import KeffLwaPlan
+    lat, lon, q = synth_c4(3, 181, 360)
+    dA = O.latlon_cell_area(lat, lon).astype(np.float32)
+    plan = KeffLwaPlan(lat, lon, dA, 91, increase=True, lt=True)
+    a = {k: v.cpu().numpy() for k, v in plan.run(dev(ops, q)).items()}
+    torch.cuda.synchronize()
+    plan.dA_row = None                                          # no row-constancy hint: general kernels
+    b = {k: v.cpu().numpy() for k, v in plan.run(dev(ops, q)).items()}
+    torch.cuda.synchronize()
+    for k in ("area", "intgrdS"):
+        pa, pb = np.diff(a[k], axis=1, prepend=0.0), np.diff(b[k], axis=1, prepend=0.0)
+        cum = np.maximum.accumulate(np.abs(b[k]), axis=1)
+        assert np.all(np.abs(pa - pb) <= 1e-13 * np.abs(pb) + 4e-16 * cum), k
+    assert np.array_equal(a["ctr"], b["ctr"])
+
+
+def test_c5_keff_in_flight_cartesian(ops):
+    """BASELINE config 5 through the fused batch (Keff part, no LWA): 4096x8192 Cartesian tracer, 2048 levels,
+    |grad q|^2 in flight (periodic x, edge value in y), uniform cell area."""
+    from xcontour_b200.pipeline import KeffLwaPlan
+    from xcontour_b200.utils import row_metrics_cartesian
+    ny, nx, N = 4096, 8192, 2048
+    y, x, q = _c5_field(1, ny, nx)
+    dA = np.full((ny, nx), 1.0 / (ny * nx))
+    cx, cy = row_metrics_cartesian(y, x)
+    plan = KeffLwaPlan(y, x, dA, N, increase=True, lt=True, metrics=(cx, cy), boundary=("periodic", "extend"))
+    assert plan.uniform_dA and not plan.any_degenerate
+    out = plan.alloc_outputs(1, lwa=False)
+    plan.run(dev(ops, q), out=out)
+    torch.cuda.synchronize()
+    grd = O.squared_gradient(q, cx, cy, "periodic", "extend")
+    ctr = O.cal_contours(q, N, True)
+    assert np.array_equal(out["ctr"].cpu().numpy().astype(np.float32), ctr)
+    area = O.cal_integral_within_contours_hist(q, ctr, dA, True)
+    intg = O.cal_integral_within_contours_hist(q, ctr, dA, True, integrand=grd)
+    assert relmax(out["area"].cpu().numpy(), area) <= RTOL_INT
+    assert relmax(out["intgrdS"].cpu().numpy(), intg) <= RTOL_INT
+    pa, pb = np.diff(out["intgrdS"].cpu().numpy(), axis=1, prepend=0.0), np.diff(intg, axis=1, prepend=0.0)
+    assert np.all(np.abs(pa - pb) <= 1e-11 * np.abs(pb) + 1e-15 * intg.max())

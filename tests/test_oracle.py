@@ -179,7 +179,7 @@ def test_library_builds_and_exports_every_declared_symbol():
         assert hasattr(lib, s), "missing export %s" % s
     assert set(_lib.SIGNATURES) == set(syms)
     lib.xc_abi_version.restype = ctypes.c_int
-    assert lib.xc_abi_version() == 1
+    assert lib.xc_abi_version() == 2
 
 
 def test_size_queries_and_argument_errors_without_gpu():
@@ -285,3 +285,21 @@ def test_product_cell_area_helper_matches_oracle():
     assert np.array_equal(latlon_cell_area(lat, lon), O.latlon_cell_area(lat, lon))
     assert np.array_equal(latlon_cell_area(lat[::-1], lon), O.latlon_cell_area(lat[::-1], lon))
     assert abs(latlon_cell_area(lat, lon).sum() / (4 * np.pi * O.Rearth ** 2) - 1) < 1e-12
+
+
+def test_general_stencil_reduces_to_the_latlon_statement_and_pads_like_numpy():
+    """oracle.squared_gradient (ghost cells by np.pad) == squared_gradient_latlon for (periodic, extend) with
+    lat-lon metrics; spot values of the other ghost-cell rules."""
+    rng = np.random.default_rng(5)
+    lat = np.linspace(-90, 90, 19); lon = np.arange(36) * 10.0
+    q = rng.standard_normal((2, 19, 36)).astype(np.float32)
+    cx, cy = O.row_metrics_latlon(lat, lon)
+    assert np.array_equal(O.squared_gradient(q, cx, cy, "periodic", "extend"), O.squared_gradient_latlon(q, lat, lon))
+    y = np.arange(19) * 2.0; x = np.arange(36) * 0.5
+    cx, cy = O.row_metrics_cartesian(y, x)
+    q64 = q.astype(np.float64)
+    g = O.squared_gradient(q, cx, cy, "reflect", "fill", fill=2.0)
+    assert g[0, 3, 0] == ((q64[0, 3, 1] - q64[0, 3, 1]) * cx[3]) ** 2 + ((q64[0, 4, 0] - q64[0, 2, 0]) * cy[3]) ** 2
+    assert g[1, 0, 5] == ((q64[1, 0, 6] - q64[1, 0, 4]) * cx[0]) ** 2 + ((q64[1, 1, 5] - 2.0) * cy[0]) ** 2
+    g = O.squared_gradient(q, cx, cy, "extend", "periodic")
+    assert g[0, 18, 35] == ((q64[0, 18, 35] - q64[0, 18, 34]) * cx[18]) ** 2 + ((q64[0, 0, 35] - q64[0, 17, 35]) * cy[18]) ** 2

@@ -41,6 +41,9 @@ class KeffLwaArgs(Structure):
         ("dqdA", c_void_p), ("Leq2", c_void_p), ("nkeff", c_void_p),
         ("Qref", c_void_p), ("lwa", c_void_p),
         ("stage_ms", c_void_p),
+        ("cx", c_void_p), ("cy", c_void_p), ("bcx", c_int), ("bcy", c_int), ("fill_value", c_double),
+        ("dA_row", c_void_p), ("uniform_dA", c_int), ("any_degenerate", c_int),
+        ("ww_row", c_void_p),
     ]
 
 

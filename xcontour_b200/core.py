@@ -85,18 +85,32 @@ class Contour2D(object):
 
     def _dev_field(self, da, key=None):
         """(tensor [S, n0, n1] on the GPU, lead dims, plane dims).  The upload of
-        ``self.tracer`` / ``self.dA`` is cached."""
-        if key is not None and key in self._cache:
-            return self._cache[key]
+        ``self.tracer`` / ``self.dA`` is cached for as long as the attribute refers to
+        the same array object (the attributes are public and may be reassigned, as in
+        the reference).  Values that already live in torch / behind DLPack (the
+        stand-in DataArray keeps them as they are) go to the kernels without a host
+        round trip."""
+        if key is not None:
+            hit = self._cache.get(key)
+            if hit is not None and hit[0] is da:
+                return hit[1]
         lead, plane = self._layout(da)
-        vals = da.values
-        if list(da.dims) != lead + plane:
-            vals = np.transpose(vals, [da.dims.index(d) for d in lead + plane])
-        t = ops.as_float(ops.to_dev(vals))
+        perm = [da.dims.index(d) for d in lead + plane]
+        raw = getattr(da, '_raw', None)
+        if raw is not None:
+            t = ops.to_dev(raw)
+            if perm != list(range(len(perm))):
+                t = t.permute(perm)
+        else:
+            vals = da.values
+            if perm != list(range(len(perm))):
+                vals = np.transpose(vals, perm)
+            t = ops.to_dev(vals)
+        t = ops.as_float(t)
         t = t.reshape((-1,) + tuple(t.shape[-2:])).contiguous()
         res = (t, lead, plane)
         if key is not None:
-            self._cache[key] = res
+            self._cache[key] = (da, res)
         return res
 
     def _tracer_dev(self, tracer=None):
@@ -104,31 +118,42 @@ class Contour2D(object):
             return self._dev_field(self.tracer, 'tracer')
         return self._dev_field(tracer)
 
-    def _dA_plane(self, plane):
-        """dA broadcast to the plane (host, its own dtype) and uploaded once."""
-        key = ('dA',) + tuple(plane)
-        if key not in self._cache:
-            dA = self.dA
-            if xc.is_labeled(dA):
-                vals = np.asarray(dA.values)
-                ddims = list(dA.dims)
-                keep = [i for i, d in enumerate(ddims) if d in plane]
-                if len(keep) != len(ddims):          # drop singleton non-plane dims
-                    vals = vals.reshape([vals.shape[i] for i in keep])
-                    ddims = [ddims[i] for i in keep]
-                order = [d for d in plane if d in ddims]
-                vals = np.transpose(vals, [ddims.index(d) for d in order])
-                shp = [vals.shape[order.index(d)] if d in order else 1 for d in plane]
-                vals = vals.reshape(shp)
-            else:
-                vals = np.asarray(dA)
-            n0 = self.tracer.shape[self.tracer.dims.index(plane[0])]
-            n1 = self.tracer.shape[self.tracer.dims.index(plane[1])]
-            vals = np.ascontiguousarray(np.broadcast_to(vals, (n0, n1)))
-            if vals.dtype not in (np.float32, np.float64):
-                vals = vals.astype(np.float64)
-            self._cache[key] = (ops.to_dev(vals), vals)
-        return self._cache[key]
+    def _dA_plane(self, plane, like=None):
+        """dA broadcast to the plane (host, its own dtype) and uploaded once per dA object.
+        ``like``: the tracer whose plane shape applies (default: self.tracer).  Cell areas
+        that vary along a non-plane dimension (time- or level-dependent, partial cells)
+        are not supported by the kernels: they raise instead of failing inside NumPy."""
+        trc = self.tracer if like is None else like
+        n0 = trc.shape[trc.dims.index(plane[0])]
+        n1 = trc.shape[trc.dims.index(plane[1])]
+        key = ('dA',) + tuple(plane) + (n0, n1)
+        hit = self._cache.get(key)
+        if hit is not None and hit[0] is self.dA:
+            return hit[1]
+        dA = self.dA
+        if xc.is_labeled(dA):
+            vals = np.asarray(dA.values)
+            ddims = list(dA.dims)
+            keep = [i for i, d in enumerate(ddims) if d in plane]
+            if len(keep) != len(ddims):          # drop singleton non-plane dims
+                extra = [ddims[i] for i in range(len(ddims)) if i not in keep and vals.shape[i] != 1]
+                if extra:
+                    raise Exception('dA varies along %s: cell areas must be constant along every '
+                                    'dimension outside the 2D plane %s' % (extra, list(plane)))
+                vals = vals.reshape([vals.shape[i] for i in keep])
+                ddims = [ddims[i] for i in keep]
+            order = [d for d in plane if d in ddims]
+            vals = np.transpose(vals, [ddims.index(d) for d in order])
+            shp = [vals.shape[order.index(d)] if d in order else 1 for d in plane]
+            vals = vals.reshape(shp)
+        else:
+            vals = np.asarray(dA)
+        vals = np.ascontiguousarray(np.broadcast_to(vals, (n0, n1)))
+        if vals.dtype not in (np.float32, np.float64):
+            vals = vals.astype(np.float64)
+        res = (ops.to_dev(vals), vals)
+        self._cache[key] = (dA, res)
+        return res
 
     def _lead_coords(self, da, lead):
         return xc.coords_for(da, lead)
@@ -266,7 +291,7 @@ class Contour2D(object):
         if edges.shape[0] == 1 and S > 1:
             edges = np.broadcast_to(edges, (S, N + 1)).copy()
             decreasing = np.broadcast_to(decreasing, (S,)).copy()
-        dA_dev, dA_np = self._dA_plane(plane)
+        dA_dev, dA_np = self._dA_plane(plane, trc)
         integ = []
         res_dtype = np.result_type(trc.dtype, dA_np.dtype)
         if integrand is not None:
@@ -307,7 +332,7 @@ class Contour2D(object):
             else XC_F64
         edges, decr = ops.hist_edges(ops.to_dev(levels.astype(np.float64)), ctr_code,
                                      time_branch=per_slice and NUMPY_SCALAR_RULES != "numpy2")
-        dA_dev, dA_np = self._dA_plane(plane)
+        dA_dev, dA_np = self._dA_plane(plane, trc)
         integ = []
         if integrand is not None:
             g, _, _ = self._dev_field(integrand)
@@ -496,14 +521,16 @@ class Contour2D(object):
         qt, lead, plane = self._tracer_dev(q)
         S = qt.shape[0]
         eq_first = plane[0] == self.dimEqV
-        dA_dev, _ = self._dA_plane(plane)
+        dA_src, _ = self._dA_plane(plane, q)
+        dA_dev = dA_src
         if not eq_first:                      # kernels want the equivalent dim first
             qt = qt.transpose(1, 2).contiguous()
             dA_dev = dA_dev.transpose(0, 1).contiguous()
-        key = ('ww', eq_first) + tuple(plane)
-        if key not in self._cache:
-            self._cache[key] = ops.lwa_weights(dA_dev.reshape(-1))
-        ww = self._cache[key]
+        key = ('ww', eq_first) + tuple(plane) + tuple(dA_src.shape)
+        hit = self._cache.get(key)
+        if hit is None or hit[0] is not dA_src:          # rebuilt whenever the dA upload was
+            hit = self._cache[key] = (dA_src, ops.lwa_weights(dA_dev.reshape(-1)))
+        ww = hit[1]
         # the sorted profile, [S, n_eq] fp64
         Qlead = [d for d in Q.dims if d != self.dimEqV]
         Qv = np.asarray(Q.values, dtype=np.float64)

@@ -102,7 +102,8 @@ extern "C" int xc_keff_lwa_batch(const xc_keff_lwa_args* a, void* workspace, siz
                "xc_keff_lwa_batch: null input pointer");
     XC_REQUIRE(a->S > 0 && a->n_y >= 2 && a->n_x >= 2 && a->N >= 2 && a->n_table >= 1,
                "xc_keff_lwa_batch: bad sizes");
-    XC_REQUIRE(a->grdS || a->lat_rad, "xc_keff_lwa_batch: need grdS or lat_rad for the stencil");
+    XC_REQUIRE(a->grdS || a->lat_rad || (a->cx && a->cy), "xc_keff_lwa_batch: need grdS, lat_rad or (cx, cy) for the stencil");
+    XC_REQUIRE(a->bcx >= 0 && a->bcx <= XC_BC_FILL && a->bcy >= 0 && a->bcy <= XC_BC_FILL, "xc_keff_lwa_batch: bad boundary condition");
     XC_REQUIRE(a->q_dtype == XC_F32 || a->q_dtype == XC_F64, "xc_keff_lwa_batch: bad q dtype");
     const long S = a->S; const int ny = a->n_y, nx = a->n_x, N = a->N;
     const long P = (long)ny * nx;
@@ -136,7 +137,11 @@ extern "C" int xc_keff_lwa_batch(const xc_keff_lwa_args* a, void* workspace, siz
     XC_REQUIRE(ar.ok(), "xc_keff_lwa_batch: workspace accounting error");
 
     StencilArgs sa; sa.ny = ny; sa.nx = nx; sa.cx = rcos; sa.cy = dphi;
-    if (stencil) { if (row_metrics(a->lat_rad, ny, a->dlambda, rcos, dphi, stream)) return 1; }
+    if (stencil && a->cx && a->cy) {
+        sa.cx = a->cx; sa.cy = a->cy; sa.bcx = a->bcx; sa.bcy = a->bcy; sa.fill = (float)a->fill_value;
+        sa.any_degenerate = a->any_degenerate;
+    } else if (stencil) { if (row_metrics(a->lat_rad, ny, a->dlambda, rcos, dphi, stream)) return 1; }
+    sa.dA_row = a->dA_row; sa.uniform_dA = a->uniform_dA;
     if (a->lwa) { if (lwa_wmax(a->ww, P, wmaxp, stream)) return 1; }      // once per call, before the passes fork
     cudaStream_t st = (cudaStream_t)stream;
     const long npass = (S + pl.sub - 1) / pl.sub;
@@ -188,6 +193,7 @@ extern "C" int xc_keff_lwa_batch(const xc_keff_lwa_args* a, void* workspace, siz
         const void* integs[1] = { stencil ? nullptr : (const void*)((const char*)a->grdS + (size_t)s0 * P * gsz) };
         const int integ_dt[1] = { a->grdS_dtype };
         HistOnly ho;
+        sa.minmax = L.minmax;
         if (bin_accumulate_impl(q, a->q_dtype, ns, P, L.edges, N + 1, N, 0, a->dA, a->dA_dtype, 1,
                                 integs, integ_dt, stencil ? 0 : 1, nullptr,
                                 a->lt ? XC_SCAN_PREFIX : XC_SCAN_TOTAL_MINUS, L.decr,

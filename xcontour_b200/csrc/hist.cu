@@ -531,6 +531,17 @@ int xc::bin_accumulate_impl(const void* q, int q_dtype, long S, long P,
     // the fused Keff pass (fp32 tracer and areas, {dA, |grad q|^2 dA}, uniform per-slice
     // edges, no mask / bin output) has a dedicated lean kernel
     if (hist_only && stencil && acc_area && n_int == 0 && !q_mask && !bin_idx && !closed_right &&
+        edges_stride == N + 1 && stencil->dA_row && stencil->minmax) {
+        int Cr = 0;
+        const int r = bin_rows_try(q, q_dtype, S, edges, N, stencil, stencil->minmax, hp.part,
+                                   (size_t)S * pl.C * K * N, &Cr, stream);
+        if (r == 2) return 1;
+        if (r == 0) { hist_only->part = hp.part; hist_only->C = Cr; return 0; }
+    }
+    const bool plain_latlon = stencil && stencil->bcx == XC_BC_PERIODIC && stencil->bcy == XC_BC_EXTEND;
+    XC_REQUIRE(!stencil || plain_latlon, "xc_bin_accumulate: ghost-cell rules other than (periodic, extend) need an fp32 "
+               "tracer with nx %% 4 == 0 and cell areas that are constant along x (dA_row)");
+    if (hist_only && plain_latlon && acc_area && n_int == 0 && !q_mask && !bin_idx && !closed_right &&
         edges_stride == N + 1 && pl.priv) {
         const int r = hist_keff_try(q, q_dtype, S, P, edges, N, dA, dA_dtype, stencil, pl.C, hp.part, stream);
         if (r == 2) return 1;

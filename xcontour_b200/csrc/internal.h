@@ -11,7 +11,16 @@ struct ScanOut { double* p[4]; long stride; };
 
 // optional in-flight |grad q|^2 integrand for bin_accumulate_impl (adds one
 // accumulator after the explicit integrands); rcos/dphi from row_metrics().
-struct StencilArgs { int ny, nx; const double* cx; const double* cy; };
+// cx/cy: [ny] row metrics, dq/dx = (q[i+1]-q[i-1])*cx[j], dq/dy = (q[j+1]-q[j-1])*cy[j]; ghost cells by bcx/bcy
+// (XC_BC_*).  dA_row (nullable): [ny] fp64 cell area of each row when dA is constant along rows -- enables the
+// row-march binning kernel (bin_rows.cu); uniform_dA: all rows equal; any_degenerate: reserve the pole-row
+// accumulator; minmax (nullable): [S][2] NaN-skipping (min, max) of each slice of this call.
+struct StencilArgs {
+    int ny, nx; const double* cx; const double* cy;
+    int bcx = XC_BC_PERIODIC, bcy = XC_BC_EXTEND; float fill = 0.f;
+    const double* dA_row = nullptr; int uniform_dA = 0, any_degenerate = 1;
+    const double* minmax = nullptr;
+};
 int row_metrics(const double* lat_rad, int ny, double dlambda, double* cx, double* cy, void* stream);
 
 struct HistOnly;
@@ -42,6 +51,11 @@ int scan_epilogue(const double* part, int C, long S, int N, int lt, const int32_
 int hist_keff_try(const void* q, int q_dtype, long S, long P, const double* edges, int N,
                   const void* dA, int dA_dtype, const StencilArgs* st, int C,
                   double* part, void* stream);
+
+// row-march fused-Keff binning kernel (bin_rows.cu): 0 launched (*C_out CTAs per slice), 1 not applicable, 2 error
+int bin_rows_try(const void* q, int q_dtype, long S, const double* edges, int N,
+                 const StencilArgs* st, const double* minmax, double* part, size_t part_doubles,
+                 int* C_out, void* stream);
 
 // levels (+ optional per-'time'-branch edges in the same launch); clears *flag_to_clear
 int minmax_levels_impl(const void* q, int q_dtype, long S, long P, int N, int increase, int out_dtype,

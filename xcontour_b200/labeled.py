@@ -18,22 +18,37 @@ def _as_np(x):
     return np.asarray(x)
 
 
+def _device_array(x):
+    """torch.Tensor for data that lives in (or is only reachable through) torch / DLPack, else None.
+    Such data is kept as it is -- Contour2D hands it to the kernels without a host round trip -- and
+    is only copied to a NumPy array when somebody asks for ``.values``."""
+    if isinstance(x, (np.ndarray, np.generic, list, tuple, float, int)):
+        return None
+    if type(x).__module__.split(".")[0] == "torch":
+        return x
+    if hasattr(x, "__dlpack__") and not hasattr(x, "__array__") and not hasattr(x, "__array_interface__"):
+        import torch
+        return torch.from_dlpack(x)
+    return None
+
+
 class DataArray(object):
     def __init__(self, data, dims=None, coords=None, name=None, attrs=None):
         if isinstance(data, DataArray):
             dims = data.dims if dims is None else dims
             coords = dict(data.coords) if coords is None else coords
             name = data.name if name is None else name
-            data = data.values
-        data = np.asarray(data)
+            data = data.values if data._raw is None else data._raw
+        self._raw = _device_array(data)            # torch tensor (any device) or None
+        self._np = None if self._raw is not None else np.asarray(data)
+        data = self._raw if self._raw is not None else self._np
         if dims is None:
             dims = tuple("dim_%d" % i for i in range(data.ndim))
         if isinstance(dims, str):
             dims = (dims,)
         dims = tuple(dims)
-        if len(dims) != data.ndim:
-            raise ValueError("dims %s do not match data of shape %s" % (dims, data.shape))
-        self._data = data
+        if len(dims) != len(data.shape):
+            raise ValueError("dims %s do not match data of shape %s" % (dims, tuple(data.shape)))
         self.dims = dims
         self.name = name
         self.attrs = dict(attrs or {})
@@ -47,31 +62,39 @@ class DataArray(object):
 
     # ---- basic protocol ----------------------------------------------------
     @property
+    def _data(self):
+        if self._np is None:                       # device-backed: materialise on first host access
+            self._np = self._raw.detach().cpu().numpy()
+        return self._np
+
+    @property
     def values(self):
         return self._data
 
     @property
     def data(self):
-        return self._data
+        return self._data if self._raw is None else self._raw
 
     @property
     def shape(self):
-        return self._data.shape
+        return tuple(self._raw.shape) if self._raw is not None else self._np.shape
 
     @property
     def dtype(self):
+        if self._raw is not None and self._np is None:
+            return np.dtype(str(self._raw.dtype).replace("torch.", ""))
         return self._data.dtype
 
     @property
     def ndim(self):
-        return self._data.ndim
+        return len(self.shape)
 
     @property
     def size(self):
-        return self._data.size
+        return int(np.prod(self.shape, dtype=np.int64))
 
     def __len__(self):
-        return self._data.shape[0]
+        return self.shape[0]
 
     def __array__(self, dtype=None, copy=None):
         return self._data if dtype is None else self._data.astype(dtype)
@@ -129,7 +152,9 @@ class DataArray(object):
             idx = tuple(key.get(d, slice(None)) for d in self.dims)
         else:
             idx = key
-        self._data[idx] = _as_np(value)
+        data = self._data
+        self._raw = None                           # a host-side edit ends the device-backed life of the array
+        data[idx] = _as_np(value)
 
     def isel(self, indexers=None, **kw):
         indexers = dict(indexers or {}, **kw)

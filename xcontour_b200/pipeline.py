@@ -25,6 +25,7 @@ import numpy as np
 import torch
 
 from . import _lib, ops
+from .utils import BOUNDARY, row_metrics_latlon
 from ._lib import KeffLwaArgs, PART, SCAN_PREFIX, SCAN_TOTAL_MINUS, XC_F32, XC_F64, check
 
 CONTOUR_VARS = ("ctr", "area", "intgrdS", "latEq", "Lmin", "dintSdA", "dqdA", "Leq2", "nkeff")
@@ -42,7 +43,12 @@ class KeffLwaPlan(object):
     table, LWA weights -- built once, reused for every batch."""
 
     def __init__(self, lat_deg, lon_deg, dA, N, increase=True, lt=True,
-                 dtype=np.float32, keff_mask=1e5, part="all", mask=None, sub_batch=0):
+                 dtype=np.float32, keff_mask=1e5, part="all", mask=None, sub_batch=0,
+                 metrics=None, boundary=("periodic", "extend"), fill_value=0.0):
+        """lat_deg / lon_deg: the equivalent (row) coordinate and the column coordinate of the plane.
+        metrics: (cx[ny], cy[ny]) row metrics of the |grad q|^2 stencil (utils.row_metrics_cartesian for
+        Cartesian / X-Z planes); default: the lat-lon metrics of utils.row_metrics_latlon.
+        boundary: ghost-cell rule along (x, y), each one of utils.BOUNDARY; fill_value for 'fill'."""
         ops.require_cuda()
         lat = np.asarray(lat_deg)
         lon = np.asarray(lon_deg)
@@ -72,6 +78,16 @@ class KeffLwaPlan(object):
         self.lat_rad = ops.to_dev(np.deg2rad(lat.astype(np.float64)))
         lam = np.deg2rad(lon.astype(np.float64))
         self.dlambda = float(lam[1] - lam[0])
+        # stencil metrics on the host (ny values each) and the hints that select the fast kernels
+        cx, cy = row_metrics_latlon(lat, lon) if metrics is None else (np.asarray(m, np.float64) for m in metrics)
+        self.cx, self.cy = ops.to_dev(np.ascontiguousarray(cx)), ops.to_dev(np.ascontiguousarray(cy))
+        self.bcx, self.bcy = BOUNDARY[boundary[0]], BOUNDARY[boundary[1]]
+        self.fill_value = float(fill_value)
+        with np.errstate(invalid="ignore", over="ignore"):
+            self.any_degenerate = bool(np.any(~np.isfinite(cx) | ~np.isfinite(cy) | ((cx * cx > 2.0 ** 30 * cy * cy) & (cy != 0))))
+        row_const = bool(np.all((dA == dA[:, :1]) | np.isnan(dA)))
+        self.dA_row = ops.to_dev(np.ascontiguousarray(dA[:, 0], dtype=np.float64)) if row_const else None
+        self.uniform_dA = bool(row_const and np.all(dA[:, 0] == dA[0, 0]))
 
     def workspace_bytes(self, S):
         return _lib.load().xc_keff_lwa_batch_workspace_bytes(S, self.ny, self.nx, self.N)
@@ -107,6 +123,10 @@ class KeffLwaPlan(object):
         else:
             a.grdS, a.grdS_dtype = None, XC_F64
         a.lat_rad, a.dlambda = self.lat_rad.data_ptr(), self.dlambda
+        a.cx, a.cy, a.bcx, a.bcy, a.fill_value = self.cx.data_ptr(), self.cy.data_ptr(), self.bcx, self.bcy, self.fill_value
+        a.dA_row = self.dA_row.data_ptr() if self.dA_row is not None else None
+        a.uniform_dA, a.any_degenerate = int(self.uniform_dA), int(self.any_degenerate)
+        a.ww_row = None
         a.table, a.table_coord, a.n_table = self.table.data_ptr(), self.table_coord.data_ptr(), self.ny
         a.eq_coord, a.ww = self.eq_coord.data_ptr(), self.ww.data_ptr()
         a.keff_mask, a.part, a.sub_batch = self.keff_mask, self.part, self.sub_batch

@@ -53,3 +53,38 @@ def latlon_cell_area(lat_deg, lon_deg, Rearth=Rearth):
         band = band[::-1]
     dlam = np.deg2rad(abs(lon[1] - lon[0]))
     return np.repeat((band * dlam)[:, None], len(lon), axis=1)
+
+
+BOUNDARY = {"periodic": 0, "extend": 1, "reflect": 2, "fill": 3}   # XC_BC_* of include/xcb200.h
+
+
+def row_metrics_latlon(lat_deg, lon_deg, Rearth=Rearth):
+    """Row metrics (cx, cy) of the centred-difference |grad q|^2 stencil on a regular lat-lon grid:
+        dq/dx = (q[j,i+1] - q[j,i-1]) * cx[j],  cx = 1 / ((2 dlambda) (R cos phi_j))
+        dq/dy = (q[j+1,i] - q[j-1,i]) * cy[j],  cy = 1 / ((phi_{j+1} - phi_{j-1}) R)   (one-sided at the ends)
+    Host-side setup (ny values), handed to the kernels as fp64 arrays.  The reference's callers get this field
+    from xinvert / GeoApps (tests/test_Keff_ocean.py:26-32); the definition is stated in DESIGN.md."""
+    phi = np.deg2rad(np.asarray(lat_deg, dtype=np.float64))
+    lam = np.deg2rad(np.asarray(lon_deg, dtype=np.float64))
+    ny = phi.shape[0]
+    jm = np.maximum(np.arange(ny) - 1, 0)
+    jp = np.minimum(np.arange(ny) + 1, ny - 1)
+    with np.errstate(divide="ignore"):
+        cx = 1.0 / ((2.0 * (lam[1] - lam[0])) * (Rearth * np.cos(phi)))
+        cy = 1.0 / ((phi[jp] - phi[jm]) * Rearth)
+    return cx, cy
+
+
+def row_metrics_cartesian(y, x):
+    """Row metrics of the same stencil on a rectilinear Cartesian / X-Z grid with coordinates y[ny] (rows, may be
+    non-uniform or descending) and uniform x[nx]: cx = 1 / (2 dx), cy[j] = 1 / (y[j+1] - y[j-1]) with the
+    interior spacing continued at the first / last row (so that every ghost-cell rule of BOUNDARY sees 2*dy)."""
+    y = np.asarray(y, dtype=np.float64)
+    x = np.asarray(x, dtype=np.float64)
+    ny = y.shape[0]
+    d = np.empty(ny)
+    d[1:-1] = y[2:] - y[:-2]
+    d[0] = 2.0 * (y[1] - y[0])
+    d[-1] = 2.0 * (y[-1] - y[-2])
+    with np.errstate(divide="ignore"):
+        return np.full(ny, 1.0 / (2.0 * (x[1] - x[0]))), 1.0 / d
