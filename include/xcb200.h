@@ -142,6 +142,17 @@ int xc_gradient_wrt_area(const void* var, int var_dtype,
                          const void* area, int area_dtype,
                          long S, int N, double* out, void* stream);
 
+/* (4b) the same against an explicit contour coordinate (ABI 2): var.differentiate('contour') is np.gradient
+ *   against the array's own 'contour' coordinate values (core.py:480-483), which are the level values when the
+ *   caller passed explicit -- possibly non-uniform -- levels to cal_contours (core.py:253-264).  The O(N)
+ *   difference coefficients are NumPy's own, computed on the host in the coordinate's dtype and handed over as
+ *   fp64 [*_coef_f32: they hold fp32 values]: uniform spacing -> {2*dx, dx}; otherwise
+ *   {a[N-2], b[N-2], c[N-2], dx_0, dx_n} (numpy.gradient, edge_order = 1).  var / area dtype: XC_F32 / XC_F64
+ *   arrays; out fp64 [S][N] holding values rounded to the promoted dtype. */
+int xc_gradient_wrt_area_coord(const void* var, int var_dtype, const double* var_coef, int var_uniform, int var_coef_f32,
+                               const void* area, int area_dtype, const double* area_coef, int area_uniform, int area_coef_f32,
+                               long S, int N, double* out, void* stream);
+
 /* ------------------------------------------------------------------------
  * (5) Keff epilogue, all fp64 element-wise over n values:
  *   xc_leq2 : Leq2  = dgrdSdA / (dqdA*dqdA)                 core.py:635
@@ -179,6 +190,13 @@ int xc_lwa(const void* q, int q_dtype, long S, int n_eq, int n_x,
            const double* Qref, const double* ww,
            int increase, int part, int variant,
            double* out, void* workspace, size_t ws_bytes, void* stream);
+/* xc_lwa_ex (ABI 2): xc_lwa with the optional hint ww_row[n_eq] fp64 = the value of ww along each row when the
+ * weights are constant along x (every regular lat-lon / Cartesian / X-Z grid); selects the column-tile kernel
+ * whose own-slot deposits stay in registers.  Same results; ww_row == NULL is xc_lwa. */
+int xc_lwa_ex(const void* q, int q_dtype, long S, int n_eq, int n_x,
+              const double* Qref, const double* ww, const double* ww_row,
+              int increase, int part, int variant,
+              double* out, void* workspace, size_t ws_bytes, void* stream);
 int xc_lwa_mask(const void* q, int q_dtype, long S, int n_eq, int n_x,
                 const double* Qref, int j, int increase, int variant,
                 int8_t* mask, void* stream);

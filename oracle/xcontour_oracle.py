@@ -328,13 +328,16 @@ def weighted_quantile_levels(q2d, dA, fractions):
 # --------------------------------------------------------------------------
 # d/dA, Leq2, Keff            xcontour/core.py:463-488, 619-637, 945-966
 # --------------------------------------------------------------------------
-def cal_gradient_wrt_area(var, area, dtype=np.float32):
-    """core.py:480-483: ``differentiate('contour')`` is np.gradient against the
-    float contour coordinate 0..N-1 (edge_order=1), each in its own dtype."""
+def cal_gradient_wrt_area(var, area, dtype=np.float32, var_coord=None, area_coord=None):
+    """core.py:480-483: ``differentiate('contour')`` is np.gradient (edge_order=1) against each array's own
+    'contour' coordinate -- the float coordinate 0..N-1 after cal_contours(int) (default here), the level values
+    themselves after cal_contours(array) (core.py:253-264) -- each in its own dtype."""
     var = np.asarray(var)
     area = np.asarray(area)
     coord = contour_coord(var.shape[-1], dtype)
-    return np.gradient(var, coord, axis=-1) / np.gradient(area, coord, axis=-1)
+    vc = coord if var_coord is None else np.asarray(var_coord)
+    ac = coord if area_coord is None else np.asarray(area_coord)
+    return np.gradient(var, vc, axis=-1) / np.gradient(area, ac, axis=-1)
 
 
 def cal_sqared_equivalent_length(dgrdSdA, dqdA):

@@ -6,7 +6,7 @@ the whole stack (partitioning must not change any result).
 import os, sys
 import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import xcontour_oracle as O
+from xcontour_b200.utils import latlon_cell_area
 from xcontour_b200 import ops
 from xcontour_b200.pipeline import KeffLwaPlan, slice_range, gather_contour_space, CONTOUR_VARS
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -18,7 +18,7 @@ rng = np.random.default_rng(5)
 phi, lam = np.deg2rad(lat)[:, None], np.deg2rad(lon)[None, :]
 q = np.stack([np.sin(phi) + 0.3 * np.cos(phi) ** 2 * np.sin(6 * lam + s) + 0.02 * rng.standard_normal((ny, nx))
               for s in range(S)]).astype(np.float32)
-dA = O.latlon_cell_area(lat, lon).astype(np.float32)
+dA = latlon_cell_area(lat, lon).astype(np.float32)
 plan = KeffLwaPlan(lat, lon, dA, N)
 lo, hi = slice_range(S, rank, world)
 out = plan.run(ops.to_dev(q[lo:hi])) if hi > lo else {k: torch.empty((0, N), dtype=torch.float64, device="cuda") for k in CONTOUR_VARS}

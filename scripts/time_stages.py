@@ -4,13 +4,13 @@ import ctypes, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
-from oracle import xcontour_oracle as O
+from xcontour_b200.utils import latlon_cell_area
 from xcontour_b200._lib import N_STAGES, STAGE_NAMES
 from xcontour_b200.pipeline import KeffLwaPlan
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 sub = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 lat, lon = bench.grid()
-dA = O.latlon_cell_area(lat, lon).astype(np.float32)
+dA = latlon_cell_area(lat, lon).astype(np.float32)
 plan = KeffLwaPlan(lat, lon, dA, bench.NLEV, sub_batch=sub)
 g = torch.Generator(device="cuda"); g.manual_seed(1)
 phi = torch.deg2rad(torch.tensor(lat, dtype=torch.float64, device="cuda"))[:, None]

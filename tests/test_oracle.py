@@ -303,3 +303,18 @@ def test_general_stencil_reduces_to_the_latlon_statement_and_pads_like_numpy():
     assert g[1, 0, 5] == ((q64[1, 0, 6] - q64[1, 0, 4]) * cx[0]) ** 2 + ((q64[1, 1, 5] - 2.0) * cy[0]) ** 2
     g = O.squared_gradient(q, cx, cy, "extend", "periodic")
     assert g[0, 18, 35] == ((q64[0, 18, 35] - q64[0, 18, 34]) * cx[18]) ** 2 + ((q64[0, 0, 35] - q64[0, 17, 35]) * cy[18]) ** 2
+
+
+def test_gradient_wrt_area_uses_the_contour_coordinate():
+    """np.gradient against non-uniform level values (what differentiate('contour') does after cal_contours(array),
+    core.py:264, 480-483) is not the unit-spacing quotient; against 0..N-1 it is."""
+    rng = np.random.default_rng(9)
+    lev = np.cumsum(0.5 + rng.random(12))
+    f = np.sin(lev); a = np.cumsum(rng.random(12))
+    got = O.cal_gradient_wrt_area(f, a, var_coord=lev, area_coord=lev)
+    hd, hs = lev[2:] - lev[1:-1], lev[1:-1] - lev[:-2]
+    def g(y):
+        return (hs ** 2 * y[2:] + (hd ** 2 - hs ** 2) * y[1:-1] - hd ** 2 * y[:-2]) / (hs * hd * (hd + hs))
+    assert np.allclose(got[1:-1], g(f) / g(a), rtol=1e-12)
+    assert np.array_equal(O.cal_gradient_wrt_area(f, a), O.cal_gradient_wrt_area(f, a, var_coord=np.arange(12.0), area_coord=np.arange(12.0)))
+    assert not np.allclose(got[1:-1], O.cal_gradient_wrt_area(f, a)[1:-1], rtol=1e-3)

@@ -67,6 +67,8 @@ SIGNATURES = {
                           c_int, c_int, c_long, c_void_p, c_void_p]),
     "xc_gradient_wrt_area": (c_int, [c_void_p, c_int, c_void_p, c_int, c_long, c_int,
                                      c_void_p, c_void_p]),
+    "xc_gradient_wrt_area_coord": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int,
+                                           c_long, c_int, c_void_p, c_void_p]),
     "xc_leq2": (c_int, [c_void_p, c_void_p, c_long, c_void_p, c_void_p]),
     "xc_lmin": (c_int, [c_void_p, c_long, c_void_p, c_void_p]),
     "xc_nkeff": (c_int, [c_void_p, c_void_p, c_double, c_long, c_void_p, c_void_p]),
@@ -76,6 +78,8 @@ SIGNATURES = {
     "xc_lwa_workspace_bytes": (c_size_t, [c_long]),
     "xc_lwa": (c_int, [c_void_p, c_int, c_long, c_int, c_int, c_void_p, c_void_p,
                        c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "xc_lwa_ex": (c_int, [c_void_p, c_int, c_long, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                          c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "xc_lwa_mask": (c_int, [c_void_p, c_int, c_long, c_int, c_int, c_void_p, c_int, c_int, c_int,
                             c_void_p, c_void_p]),
     "xc_grad2_latlon": (c_int, [c_void_p, c_int, c_long, c_int, c_int, c_void_p, c_double,

@@ -454,7 +454,16 @@ class Contour2D(object):
         if a.shape != v.shape:
             a = np.broadcast_to(a, v.shape)
         vt, at = ops.as_float(ops.to_dev(v)), ops.as_float(ops.to_dev(a))
-        out = ops.gradient_wrt_area(vt, ops.fdtype(vt), at, ops.fdtype(at))
+        # differentiate('contour') runs against each array's own 'contour' coordinate: 0..N-1 from cal_contours(int),
+        # the level values themselves after cal_contours(array) (core.py:253-264), possibly non-uniform
+        N = v.shape[-1]
+        vcoord, acoord = xc.coord(var, 'contour'), xc.coord(area, 'contour')
+        unit = np.arange(N)
+        if (vcoord is None or np.array_equal(vcoord, unit)) and (acoord is None or np.array_equal(acoord, unit)):
+            out = ops.gradient_wrt_area(vt, ops.fdtype(vt), at, ops.fdtype(at))
+        else:
+            out = ops.gradient_wrt_area_coord(vt, unit.astype(np.float32) if vcoord is None else vcoord,
+                                              at, unit.astype(np.float32) if acoord is None else acoord)
         rdt = np.result_type(np.asarray(var.values).dtype, np.asarray(area.values).dtype)
         if rdt not in (np.float32, np.float64):
             rdt = np.float64
@@ -529,8 +538,9 @@ class Contour2D(object):
         key = ('ww', eq_first) + tuple(plane) + tuple(dA_src.shape)
         hit = self._cache.get(key)
         if hit is None or hit[0] is not dA_src:          # rebuilt whenever the dA upload was
-            hit = self._cache[key] = (dA_src, ops.lwa_weights(dA_dev.reshape(-1)))
-        ww = hit[1]
+            w = ops.lwa_weights(dA_dev.reshape(-1))
+            hit = self._cache[key] = (dA_src, w, ops.row_constant(w, dA_dev.shape[0], dA_dev.shape[1]))
+        ww, ww_row = hit[1], hit[2]
         # the sorted profile, [S, n_eq] fp64
         Qlead = [d for d in Q.dims if d != self.dimEqV]
         Qv = np.asarray(Q.values, dtype=np.float64)
@@ -538,7 +548,7 @@ class Contour2D(object):
         if Qv.shape[0] != S:
             Qv = np.broadcast_to(Qv, (S, n_eq))
         Qt = ops.to_dev(np.ascontiguousarray(Qv))
-        out = ops.lwa(qt, Qt, ww, self.increase, part, variant)
+        out = ops.lwa(qt, Qt, ww, self.increase, part, variant, ww_row=ww_row)
 
         def back(t, dtype=None):
             if not eq_first:

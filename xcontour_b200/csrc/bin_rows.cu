@@ -127,13 +127,14 @@ template <int PLW>
 __host__ __device__ inline BinRowsSmem bin_rows_layout(int N, int rows_per, int uniform_dA, int any_deg)
 {
     BinRowsSmem L; size_t o = 0;
-    L.e2 = o;   o += (size_t)((N + 1) & ~1) * 8;
-    L.acc = o;  o += (size_t)3 * PLW * 4;
-    L.esc = o;  o += (size_t)N * 8;
-    L.rowc = o; o += (size_t)rows_per * 32;                    // per row: cx', cy', dA, flag
-    L.acc2 = o; o += any_deg ? (size_t)3 * N * 4 : 0;
-    L.cnt = o;  o += (size_t)(uniform_dA ? 1 : (rows_per + 1) / 2) * N * 4;
-    L.total = (o + 15) & ~(size_t)15;
+    auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };   // every region 16-byte aligned (v2.f64 / uint4 accesses)
+    L.e2 = o;   o = al(o + (size_t)N * 8);
+    L.acc = o;  o = al(o + (size_t)3 * PLW * 4);
+    L.esc = o;  o = al(o + (size_t)N * 8);
+    L.rowc = o; o = al(o + (size_t)rows_per * 32);              // per row: cx', cy', dA, flag
+    L.acc2 = o; o = al(o + (any_deg ? (size_t)3 * N * 4 : 0));
+    L.cnt = o;  o = al(o + (size_t)(uniform_dA ? 1 : (rows_per + 1) / 2) * N * 4);
+    L.total = o;
     return L;
 }
 
@@ -316,14 +317,17 @@ k_bin_rows(const BinRowsParams p)
         const uint32_t cinc = p.uniform_dA ? 1u : 1u << ((r & 1) << 4);
         const bool normal = flag == 0.0;
         // common case of a warp step: every lane's four cells are binned and every term is in range
-        const bool ok = (b[0] | b[1] | b[2] | b[3]) >= 0 &&
+        // (lanes past the last column of the strip have nothing to add and do not spoil the vote)
+        const bool ok = !act || ((b[0] | b[1] | b[2] | b[3]) >= 0 &&
                         (unsigned)__double2hiint(G[0]) < hi_limit && (unsigned)__double2hiint(G[1]) < hi_limit &&
-                        (unsigned)__double2hiint(G[2]) < hi_limit && (unsigned)__double2hiint(G[3]) < hi_limit;
+                        (unsigned)__double2hiint(G[2]) < hi_limit && (unsigned)__double2hiint(G[3]) < hi_limit);
         if (normal && __all_sync(XC_FULL, ok)) {
+            if (act) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) br_red(crow + (uint32_t)b[c] * 4u, cinc);
+                for (int c = 0; c < 4; ++c) br_red(crow + (uint32_t)b[c] * 4u, cinc);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) br_add96<PLB>(acc_sh + (uint32_t)b[c] * (COPIES * 4u), G[c]);
+                for (int c = 0; c < 4; ++c) br_add96<PLB>(acc_sh + (uint32_t)b[c] * (COPIES * 4u), G[c]);
+            }
             return;
         }
 #pragma unroll
@@ -386,6 +390,48 @@ k_bin_rows(const BinRowsParams p)
 
 using namespace xc;
 
+namespace {
+struct BinRowsPlan { bool ok; bool small; int NT, strips, strip_w, rows_per, hbits; long C; size_t smem; };
+// uniform_dA / any_degenerate < 0: unknown (workspace sizing) -> the combination that needs the most shared memory
+BinRowsPlan bin_rows_plan(long S, int ny, int nx, int N, int uniform_dA, int any_degenerate)
+{
+    BinRowsPlan pl; pl.ok = false;
+    if ((nx & 3) || nx < 8 || ny < 2 || N < 1 || N > 2048 || S < 1) return pl;
+    const int uni = uniform_dA < 0 ? 0 : uniform_dA, deg = any_degenerate < 0 ? 1 : any_degenerate;
+    pl.small = N <= 512;
+    if (nx <= 4 * BR_MAXT) { pl.NT = ((nx / 4 + 31) / 32) * 32; pl.strips = 1; }
+    else { pl.NT = 256; pl.strips = (nx + 4 * pl.NT - 1) / (4 * pl.NT); }
+    pl.strip_w = 4 * pl.NT;
+    const long slots = (long)sm_count() * 2;
+    long per_slice = slots / S; if (per_slice < 1) per_slice = 1;
+    long rbs = per_slice / pl.strips; if (rbs < 1) rbs = 1;
+    int rows_per = (int)((ny + rbs - 1) / rbs);
+    if (rows_per < 8) rows_per = ny < 8 ? ny : 8;                  // the two halo rows of a march stay a small share
+    auto lay = [&](int rp) {
+        return pl.small ? bin_rows_layout<4 * 512>(N, rp, uni, deg).total : bin_rows_layout<2 * 2048>(N, rp, uni, deg).total;
+    };
+    const size_t budget = 110 * 1024;                                // two CTAs per SM
+    while (lay(rows_per) > budget) {
+        if (rows_per <= 2) return pl;
+        rows_per = (rows_per * 3 / 4 + 1) & ~1;
+    }
+    pl.rows_per = rows_per;
+    pl.C = (long)((ny + rows_per - 1) / rows_per) * pl.strips;
+    pl.smem = lay(rows_per);
+    const long cells = (long)rows_per * pl.strip_w;
+    pl.hbits = 12; while ((1L << pl.hbits) < cells) ++pl.hbits;     // >= 12: terms stay below 2^84 (br_add96)
+    pl.ok = pl.C <= 65535 && pl.hbits <= 30 && pl.strip_w <= 65535;
+    return pl;
+}
+}  // namespace
+
+// doubles of per-CTA partials the row-march kernel may need for S slices (0: it never applies)
+size_t xc::bin_rows_part_doubles(long S, int ny, int nx, int N)
+{
+    const BinRowsPlan pl = bin_rows_plan(S, ny, nx, N, -1, -1);
+    return pl.ok ? (size_t)S * pl.C * 2 * N : 0;
+}
+
 // Plans and launches the row-march kernel.  Returns 0 launched (C_out = CTAs per slice), 1 not applicable, 2 error.
 int xc::bin_rows_try(const void* q, int q_dtype, long S, const double* edges, int N,
                      const StencilArgs* st, const double* minmax, double* part, size_t part_doubles,
@@ -393,52 +439,31 @@ int xc::bin_rows_try(const void* q, int q_dtype, long S, const double* edges, in
 {
     if (q_dtype != XC_F32 || !st || !st->dA_row || !minmax) return 1;
     const int ny = st->ny, nx = st->nx;
-    if ((nx & 3) || nx < 8 || ny < 2 || N < 1 || N > 2048 || (((uintptr_t)q) & 15)) return 1;
+    if ((((uintptr_t)q) & 15)) return 1;
     static const char* off = getenv("XCB200_NO_BIN_ROWS");
     if (off) return 1;
-    const bool small = N <= 512;
-    int NT, strips;
-    if (nx <= 4 * BR_MAXT) { NT = ((nx / 4 + 31) / 32) * 32; strips = 1; }
-    else { NT = 256; strips = (nx + 4 * NT - 1) / (4 * NT); }
-    const int strip_w = 4 * NT;
-    const long slots = (long)sm_count() * 2;
-    long per_slice = slots / S; if (per_slice < 1) per_slice = 1;
-    long rbs = per_slice / strips; if (rbs < 1) rbs = 1; if (rbs > ny) rbs = ny;
-    int rows_per = (int)((ny + rbs - 1) / rbs);
-    const size_t budget = 110 * 1024;                          // two CTAs per SM
-    auto lay = [&](int rp) {
-        return small ? bin_rows_layout<4 * 512>(N, rp, st->uniform_dA, st->any_degenerate).total
-                     : bin_rows_layout<2 * 2048>(N, rp, st->uniform_dA, st->any_degenerate).total;
-    };
-    for (;;) {
-        if (lay(rows_per) <= budget) break;
-        if (rows_per <= 2) return 1;
-        rows_per = (rows_per * 3 / 4 + 1) & ~1;
+    BinRowsPlan pl = bin_rows_plan(S, ny, nx, N, st->uniform_dA, st->any_degenerate);
+    if (!pl.ok) return 1;
+    if ((size_t)S * pl.C * 2 * N > part_doubles) {                   // sized for the worst-case flags: cannot happen
+        set_error("k_bin_rows: partial buffer too small (%zu < %zu doubles)", part_doubles, (size_t)S * pl.C * 2 * N); return 2;
     }
-    rbs = (ny + rows_per - 1) / rows_per;
-    const long C = rbs * strips;
-    if ((size_t)S * C * 2 * N > part_doubles || C > 65535) return 1;
-    const long cells = (long)rows_per * strip_w;
-    int hbits = 12; while ((1L << hbits) < cells) ++hbits;   // >= 12: terms stay below 2^84 (br_add96)
-    if (hbits > 30 || strip_w > 65535) return 1;
     BinRowsParams p;
     p.q = (const float*)q; p.ny = ny; p.nx = nx; p.edges = edges; p.N = N;
     p.cx = st->cx; p.cy = st->cy; p.dA_row = st->dA_row; p.minmax = minmax;
     p.bcx = st->bcx; p.bcy = st->bcy; p.fill = st->fill;
-    p.strips = strips; p.rows_per = rows_per; p.strip_w = strip_w;
-    p.uniform_dA = st->uniform_dA; p.any_degenerate = st->any_degenerate; p.hbits = hbits; p.part = part;
-    const size_t smem = lay(rows_per);
-    auto kern = small ? k_bin_rows<4, 512> : k_bin_rows<2, 2048>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-        set_error("k_bin_rows: cannot reserve %zu bytes of shared memory", smem); return 2;
+    p.strips = pl.strips; p.rows_per = pl.rows_per; p.strip_w = pl.strip_w;
+    p.uniform_dA = st->uniform_dA; p.any_degenerate = st->any_degenerate; p.hbits = pl.hbits; p.part = part;
+    auto kern = pl.small ? k_bin_rows<4, 512> : k_bin_rows<2, 2048>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess) {
+        set_error("k_bin_rows: cannot reserve %zu bytes of shared memory", pl.smem); return 2;
     }
     for (long s0 = 0; s0 < S; s0 += 65535) {
         const long ns = S - s0 < 65535 ? S - s0 : 65535;
         p.s0 = s0;
-        kern<<<dim3((unsigned)C, (unsigned)ns), NT, smem, (cudaStream_t)stream>>>(p);
+        kern<<<dim3((unsigned)pl.C, (unsigned)ns), pl.NT, pl.smem, (cudaStream_t)stream>>>(p);
         count_launch();
         if (cudaGetLastError() != cudaSuccess) { set_error("k_bin_rows launch failed"); return 2; }
     }
-    *C_out = (int)C;
+    *C_out = (int)pl.C;
     return 0;
 }

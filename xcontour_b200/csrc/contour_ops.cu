@@ -68,6 +68,51 @@ __global__ void k_gradient_wrt_area(const void* __restrict__ var, int var_kind,
     }
 }
 
+// np.gradient against an explicit (possibly non-uniform) contour coordinate, edge_order = 1.  The coefficients
+// come from NumPy itself on the host (numpy/lib/_function_base_impl.py, gradient): uniform spacing ->
+// coef = {2*dx, dx}: interior (f[k+1]-f[k-1]) / (2*dx), ends (f[1]-f[0]) / dx; otherwise
+// coef = {a[N-2], b[N-2], c[N-2], dx_0, dx_n}: interior a*f[k-1] + b*f[k] + c*f[k+1].  `c32`: the coefficients are
+// fp32 values and f is fp32 -> arithmetic in fp32, else in fp64; the result is rounded to f's dtype (np.gradient
+// allocates its output in f.dtype).
+__device__ __forceinline__ double grad_coord_at(const void* f, int kind, long base, int k, int N,
+                                                const double* coef, int uniform, int c32)
+{
+    auto F = [&](int i) -> double {
+        return kind == XC_F32 ? (double)((const float*)f)[base + i] : ((const double*)f)[base + i];
+    };
+    const bool f32 = kind != XC_F64;
+    const bool in32 = f32 && c32;
+    double r;
+    if (k == 0 || k == N - 1) {
+        const double dx = uniform ? coef[1] : coef[3 * (N - 2) + (k == 0 ? 0 : 1)];
+        const double hi = F(k == 0 ? 1 : N - 1), lo = F(k == 0 ? 0 : N - 2);
+        if (f32) { const float d = __fsub_rn((float)hi, (float)lo); r = in32 ? (double)__fdiv_rn(d, (float)dx) : __ddiv_rn((double)d, dx); }
+        else r = __ddiv_rn(__dsub_rn(hi, lo), dx);
+    } else if (uniform) {
+        if (f32) { const float d = __fsub_rn((float)F(k + 1), (float)F(k - 1)); r = in32 ? (double)__fdiv_rn(d, (float)coef[0]) : __ddiv_rn((double)d, coef[0]); }
+        else r = __ddiv_rn(__dsub_rn(F(k + 1), F(k - 1)), coef[0]);
+    } else {
+        const double a = coef[k - 1], b = coef[(N - 2) + k - 1], c = coef[2 * (N - 2) + k - 1];
+        if (in32) r = (double)__fadd_rn(__fadd_rn(__fmul_rn((float)a, (float)F(k - 1)), __fmul_rn((float)b, (float)F(k))), __fmul_rn((float)c, (float)F(k + 1)));
+        else r = __dadd_rn(__dadd_rn(__dmul_rn(a, F(k - 1)), __dmul_rn(b, F(k))), __dmul_rn(c, F(k + 1)));
+    }
+    return f32 ? (double)(float)r : r;
+}
+
+__global__ void k_gradient_wrt_area_coord(const void* __restrict__ var, int var_kind, const double* __restrict__ vcoef,
+                                          int v_uniform, int v_c32,
+                                          const void* __restrict__ area, int area_kind, const double* __restrict__ acoef,
+                                          int a_uniform, int a_c32, long total, int N, double* __restrict__ out)
+{
+    const bool both32 = (var_kind != XC_F64) && (area_kind != XC_F64);
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long s = i / N; const int k = (int)(i - s * N);
+        const double dv = grad_coord_at(var, var_kind, s * N, k, N, vcoef, v_uniform, v_c32);
+        const double da = grad_coord_at(area, area_kind, s * N, k, N, acoef, a_uniform, a_c32);
+        out[i] = both32 ? (double)__fdiv_rn((float)dv, (float)da) : __ddiv_rn(dv, da);
+    }
+}
+
 __global__ void k_leq2(const double* a, const double* b, long n, double* out)
 {
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
@@ -139,6 +184,22 @@ extern "C" int xc_gradient_wrt_area(const void* var, int var_dtype,
     const long total = S * (long)N;
     k_gradient_wrt_area<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
         var, var_dtype, area, area_dtype, total, N, out);
+    XC_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int xc_gradient_wrt_area_coord(const void* var, int var_dtype, const double* var_coef, int var_uniform, int var_coef_f32,
+                                          const void* area, int area_dtype, const double* area_coef, int area_uniform, int area_coef_f32,
+                                          long S, int N, double* out, void* stream)
+{
+    XC_REQUIRE(var && area && out && var_coef && area_coef, "xc_gradient_wrt_area_coord: null pointer");
+    XC_REQUIRE(S > 0 && N >= 2, "xc_gradient_wrt_area_coord: need S>0, N>=2");
+    XC_REQUIRE((var_dtype == XC_F32 || var_dtype == XC_F64) && (area_dtype == XC_F32 || area_dtype == XC_F64),
+               "xc_gradient_wrt_area_coord: bad dtype");
+    const long total = S * (long)N;
+    k_gradient_wrt_area_coord<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+        var, var_dtype, var_coef, var_uniform, var_coef_f32, area, area_dtype, area_coef, area_uniform, area_coef_f32,
+        total, N, out);
     XC_LAUNCH_OK();
     return 0;
 }

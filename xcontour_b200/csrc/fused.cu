@@ -69,7 +69,7 @@ FusedPlan fused_plan(long S, int ny, int nx, int N, long sub_req)
     const long P = (long)ny * nx;
     p.sub = sub_req > 0 ? (sub_req < S ? sub_req : S) : auto_sub_batch(S, P);
     p.ws_minmax = xc_minmax_levels_workspace_bytes(p.sub, P);
-    p.ws_hist = xc_bin_accumulate_workspace_bytes(p.sub, P, N, 2);
+    p.ws_hist = bin_accumulate_ws_bytes_stencil(p.sub, ny, nx, N);
     p.ws_lwa = xc_lwa_workspace_bytes(p.sub) + 512;
     size_t t = 0;
     t += align_up(p.ws_minmax, 256) + align_up(p.ws_hist, 256) + align_up(p.ws_lwa, 256);
@@ -208,7 +208,7 @@ extern "C" int xc_keff_lwa_batch(const xc_keff_lwa_args* a, void* workspace, siz
         // (6) LWA
         if (a->lwa)
             if (lwa_impl(q, a->q_dtype, ns, ny, nx, Qref, a->ww, a->increase, a->part, 1,
-                         a->lwa + (size_t)s0 * P, L.sorted, L.any_unsorted, true, L.minmax, L.lwa_scratch, ps, wmaxp)) return 1;
+                         a->lwa + (size_t)s0 * P, L.sorted, L.any_unsorted, true, L.minmax, L.lwa_scratch, ps, wmaxp, a->ww_row)) return 1;
         mark(5);
         ++pass;
     }

@@ -465,6 +465,13 @@ extern "C" size_t xc_bin_accumulate_workspace_bytes(long S, long P, int N, int K
     return 256 + (size_t)S * pl.C * K * N * sizeof(double);
 }
 
+size_t xc::bin_accumulate_ws_bytes_stencil(long S, int ny, int nx, int N)
+{
+    const size_t a = xc_bin_accumulate_workspace_bytes(S, (long)ny * nx, N, 2);
+    const size_t b = 256 + bin_rows_part_doubles(S, ny, nx, N) * sizeof(double);
+    return a > b ? a : b;
+}
+
 extern "C" int xc_bin_accumulate(const void* q, int q_dtype, long S, long P,
                                  const double* edges, long edges_stride, int N,
                                  int closed_right,
@@ -510,6 +517,11 @@ int xc::bin_accumulate_impl(const void* q, int q_dtype, long S, long P,
                "xc_bin_accumulate: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     Arena ar(workspace, ws_bytes);
+    size_t part_doubles = (size_t)S * pl.C * K * N;
+    if (hist_only && stencil && ws_bytes >= bin_accumulate_ws_bytes_stencil(S, stencil->ny, stencil->nx, N)) {
+        const size_t r = bin_rows_part_doubles(S, stencil->ny, stencil->nx, N);
+        if (r > part_doubles) part_doubles = r;
+    }
     HistParams hp;
     hp.q = q; hp.P = P; hp.per = ((P + pl.C - 1) / pl.C + 3) & ~3L;
     hp.edges = edges; hp.edges_stride = edges_stride; hp.N = N; hp.closed_right = closed_right;
@@ -525,7 +537,7 @@ int xc::bin_accumulate_impl(const void* q, int q_dtype, long S, long P,
     if (stencil) {
         hp.ny = stencil->ny; hp.nx = stencil->nx; hp.cx = stencil->cx; hp.cy = stencil->cy;
     } else { hp.ny = hp.nx = 0; hp.cx = hp.cy = nullptr; }
-    hp.part = ar.take<double>((size_t)S * pl.C * K * N);
+    hp.part = ar.take<double>(part_doubles);
     hp.bin_idx = bin_idx;
     hp.ncopy = pl.ncopy;
     // the fused Keff pass (fp32 tracer and areas, {dA, |grad q|^2 dA}, uniform per-slice
@@ -534,7 +546,7 @@ int xc::bin_accumulate_impl(const void* q, int q_dtype, long S, long P,
         edges_stride == N + 1 && stencil->dA_row && stencil->minmax) {
         int Cr = 0;
         const int r = bin_rows_try(q, q_dtype, S, edges, N, stencil, stencil->minmax, hp.part,
-                                   (size_t)S * pl.C * K * N, &Cr, stream);
+                                   part_doubles, &Cr, stream);
         if (r == 2) return 1;
         if (r == 0) { hist_only->part = hp.part; hist_only->C = Cr; return 0; }
     }

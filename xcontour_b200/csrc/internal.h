@@ -34,6 +34,8 @@ int bin_accumulate_impl(const void* q, int q_dtype, long S, long P,
                         double* pdf, const ScanOut& so, int32_t* bin_idx,
                         void* workspace, size_t ws_bytes, void* stream,
                         const StencilArgs* stencil = nullptr, struct HistOnly* hist_only = nullptr);
+// workspace of bin_accumulate_impl when the caller passes stencil (ny, nx known) and hist_only
+size_t bin_accumulate_ws_bytes_stencil(long S, int ny, int nx, int N);
 
 // when passed to bin_accumulate_impl the scan kernel is skipped and the caller
 // gets the per-CTA partials [S][C][K][N] (the fused epilogue reduces them itself)
@@ -57,6 +59,8 @@ int bin_rows_try(const void* q, int q_dtype, long S, const double* edges, int N,
                  const StencilArgs* st, const double* minmax, double* part, size_t part_doubles,
                  int* C_out, void* stream);
 
+size_t bin_rows_part_doubles(long S, int ny, int nx, int N);
+
 // levels (+ optional per-'time'-branch edges in the same launch); clears *flag_to_clear
 int minmax_levels_impl(const void* q, int q_dtype, long S, long P, int N, int increase, int out_dtype,
                        double* levels, double* minmax, double* edges, int32_t* decreasing,
@@ -71,7 +75,7 @@ size_t lwa_scratch_doubles(long S, bool have_minmax);
 int lwa_impl(const void* q, int q_dtype, long S, int n_eq, int n_x, const double* Qref, const double* ww,
              int increase, int part, int variant, double* out, int32_t* sorted,
              int32_t* any_unsorted, bool flags_ready, const double* minmax, double* scratch, void* stream,
-             const double* wmax_ready = nullptr);
+             const double* wmax_ready = nullptr, const double* ww_row = nullptr);
 // partial max |ww| (lwa_wmax_doubles() values) for wmax_ready: the fused batch computes them once per call
 size_t lwa_wmax_doubles();
 int lwa_wmax(const double* ww, long P, double* parts, void* stream);

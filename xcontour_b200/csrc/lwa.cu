@@ -389,7 +389,7 @@ k_lwa_fast(const QT* __restrict__ q, long s0, int ny, int nx,
 #ifndef XC_FX_LUT            /* buckets of the LUT over Q.  The bisection that finishes the search is the most
                                 expensive source line of the kernel (9 % of its instructions, ncu source page); 4096
                                 buckets still fit the 16-column tile at ny = 721 (224 of 227 KB).  Not yet timed. */
-#define XC_FX_LUT 1024
+#define XC_FX_LUT 2048
 #endif
 constexpr int FX_SEG = 64;                 // row segments per column (threads = FX_SEG * TC)
 constexpr int FX_LUT = XC_FX_LUT;
@@ -743,6 +743,256 @@ k_lwa_fx(const QT* __restrict__ q, long s0, long sbase, int ny, int nx,
     }
 }
 
+// ---------------------------------------------------------------------------
+// Second-generation fixed-point kernel ("column tiles with register-resident own
+// deposits") for weights that are constant along a row, ww[j][i] = ww_row[j] -- every
+// regular lat-lon, Cartesian and X-Z grid.  Same arithmetic as k_lwa_fx (same scales,
+// same rounding of every term; 2^-kS is folded into the (Q_j - c) table, which is exact --
+// the two kernels agree bit for bit); what changes is where the
+// work is done (ncu of k_lwa_fx: 201 warp-instructions per 32 cells, 64 % of the time on
+// the prefix side):
+//   * no weight loads: -w 2^kV and -rn(w 2^kS) of the ny rows sit in shared memory;
+//   * a thread keeps the own-slot deposit of each of its <= 12 cells in registers
+//     between the scatter and the prefix phase (it owns the same (column, rows) in both),
+//     so the prefix walk neither re-derives it from global memory nor pays four more
+//     atomics: scatter = one 64-bit deposit per accumulator at the FAR end of the range;
+//   * lo and hi word of an accumulator are adjacent: one LDS.64 per accumulator and row
+//     in the two prefix passes, immediate offsets in the unrolled walk;
+//   * the search runs on fp32 thresholds (smallest fp32 > Q_j and >= Q_j: for an fp32
+//     value v, #{Q < v} = #{T_> <= v}), a 2048-bucket LUT bounds it to ~0.3 probes;
+//   * persistent CTAs walk consecutive tiles of the slice-major tile list, so the tables
+//     of a slice are built once per CTA and slice, not once per tile.
+// grid = SM count, block = 1024 = 16 columns x 64 row segments, one CTA per SM.
+constexpr int LC_TC = 16, LC_U = 12, LC_NT = FX_SEG * LC_TC;
+struct LwaColsSmem { size_t farS, farV, nxs, uni, total; size_t lut, ta, tb, wrow, tot, qc; };
+static __host__ __device__ inline LwaColsSmem lwa_cols_layout(int ny, int tbytes)
+{
+    LwaColsSmem L; size_t o = 0;
+    const size_t plane = (size_t)(ny + 1) * LC_TC * 8;
+    L.farS = o; o += plane;
+    L.farV = o; o += plane;
+    L.nxs = o;  o += (size_t)((ny + 1) & ~1) * 8;
+    L.uni = o;
+    size_t a = 0;                                              // scatter-phase view of the union
+    L.lut = o + a;  a += (size_t)FX_LUT * 4;
+    L.wrow = o + a; a += (size_t)((ny + 1) & ~1) * 8;
+    L.ta = o + a;   a += (size_t)((ny + 2 + 3) & ~3) * tbytes;       // two +inf entries past the end
+    L.tb = o + a;   a += (size_t)((ny + 2 + 3) & ~3) * tbytes;
+    size_t b = 0;                                              // prefix-phase view
+    L.tot = o + b;  b += (size_t)2 * LC_TC * FX_TOTP * 8;
+    L.qc = o + b;   b += (size_t)((ny + 1) & ~1) * 8;
+    L.total = o + (a > b ? a : b);
+    return L;
+}
+__device__ __forceinline__ void lc_add64(uint32_t a, long long x)
+{
+    asm volatile("{\n\t.reg .u32 o, d, h;\n\t"
+                 "atom.shared.add.u32 o, [%0], %1;\n\t"
+                 "add.cc.u32 d, o, %1;\n\t"
+                 "addc.u32 h, %2, 0;\n\t"
+                 "red.shared.add.u32 [%0+4], h;\n\t}"
+                 :: "r"(a), "r"((uint32_t)x), "r"((uint32_t)((unsigned long long)x >> 32)) : "memory");
+}
+__device__ __forceinline__ long long lc_lds64(uint32_t a)
+{
+    long long v; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(a)); return v;
+}
+// smallest value of the threshold type that is > x (strict) or >= x
+__device__ __forceinline__ float lc_thr(double x, bool strict, float)
+{
+    float f = __double2float_rn(x);
+    const bool fine = strict ? (double)f > x : (double)f >= x;
+    if (!fine) {                                                   // next float above f
+        const int b = __float_as_int(f);
+        f = (f == 0.0f) ? __int_as_float(1) : __int_as_float(f > 0.0f ? b + 1 : b - 1);
+    }
+    return f;
+}
+__device__ __forceinline__ double lc_thr(double x, bool strict, double) { return strict ? nextafter(x, CUDART_INF) : x; }
+
+__device__ __forceinline__ uint32_t lc_keep(uint32_t x) { uint32_t r; asm volatile("mov.b32 %0, %1;" : "=r"(r) : "r"(x)); return r; }
+
+// The scatter phase is written without data-dependent branches: a warp executes every path of a divergent
+// branch, and in the first version of this kernel (divergent search loops, region-1 / region-2 / inactive
+// paths, `continue`s) that made the executed warp-instruction count 2.6x the per-thread count (ncu: 199
+// warp-instructions per 32 cells, same as k_lwa_fx).  Here every cell does the same thing: two independent
+// probes after the LUT (a warp-uniform vote sends the rare denser buckets and exact ties to a loop), the target
+// slot by selects, and ALWAYS one far deposit per accumulator -- a cell without a range deposits at its own
+// slot jp + 1, where the walk's unconditional own deposit cancels it exactly (integers).
+template <typename QT, bool INC>
+__global__ void __launch_bounds__(LC_NT, 1)
+k_lwa_cols(const QT* __restrict__ q, long s0, int nslices, int ny, int nx,
+           const double* __restrict__ Qref, const double* __restrict__ ww_row,
+           int part, const int32_t* __restrict__ sorted,
+           const FxScale* __restrict__ fxs, const uint32_t* __restrict__ lutg,
+           double* __restrict__ out)
+{
+    using TT = QT;                                               // thresholds live in the tracer's own type
+    extern __shared__ __align__(16) unsigned char smem[];
+    const LwaColsSmem L = lwa_cols_layout(ny, (int)sizeof(TT));
+    long long* nxs = reinterpret_cast<long long*>(smem + L.nxs);
+    uint32_t*  lut = reinterpret_cast<uint32_t*>(smem + L.lut);
+    double*    wrow = reinterpret_cast<double*>(smem + L.wrow);
+    TT*        ta = reinterpret_cast<TT*>(smem + L.ta);
+    TT*        tb = reinterpret_cast<TT*>(smem + L.tb);
+    long long* tot = reinterpret_cast<long long*>(smem + L.tot);
+    double*    qcs = reinterpret_cast<double*>(smem + L.qc);
+    const uint32_t sm0 = (uint32_t)__cvta_generic_to_shared(smem);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr double sg = INC ? 1.0 : -1.0;
+    const bool keep_pos = (part == XC_PART_UPPER) == INC;
+    const bool use_t1 = (part == XC_PART_ALL) || !keep_pos;   // mask -1 region
+    const bool use_t2 = (part == XC_PART_ALL) || keep_pos;    // mask +1 region
+    const int c = tid & (LC_TC - 1), seg = tid / LC_TC;
+    const int r0 = (int)(((long)seg * ny) / FX_SEG), r1 = (int)(((long)(seg + 1) * ny) / FX_SEG);
+    const int tps = (nx + LC_TC - 1) / LC_TC;                  // tiles per slice
+    const long ntiles = (long)nslices * tps;
+    const long t_beg = ntiles * blockIdx.x / gridDim.x, t_end = ntiles * (blockIdx.x + 1) / gridDim.x;
+    // shared-window addresses the compiler must not rebuild from special registers at every use
+    const uint32_t farS_c = lc_keep(sm0 + (uint32_t)L.farS + (uint32_t)c * 8u);
+    const uint32_t farV_c = lc_keep(sm0 + (uint32_t)L.farV + (uint32_t)c * 8u);
+    const uint32_t colS = lc_keep(farS_c + (uint32_t)r0 * (LC_TC * 8)), colV = lc_keep(farV_c + (uint32_t)r0 * (LC_TC * 8));
+    const uint32_t nxs_r0 = lc_keep(sm0 + (uint32_t)L.nxs + (uint32_t)r0 * 8u);
+    const uint32_t wrow_r0 = lc_keep(sm0 + (uint32_t)L.wrow + (uint32_t)r0 * 8u);
+    const uint32_t qcs_r0 = lc_keep(sm0 + (uint32_t)L.qc + (uint32_t)r0 * 8u);
+
+    long cur_slice = -1;
+    double fc = 0.0, fiV = 0.0; float scalef = 0.f, qminf = 0.f;
+    bool slice_ok = false;
+    for (long tile = t_beg; tile < t_end; ++tile) {
+        const long sl = tile / tps; const int tx = (int)(tile - sl * tps);
+        const long s = s0 + sl;
+        const bool fresh = sl != cur_slice;
+        if (fresh) { cur_slice = sl; slice_ok = sorted[s] != 0; }
+        if (!slice_ok) continue;                                  // uniform: the exact loop takes this slice
+        const FxScale* fp = fxs + sl;
+        const double* Qg = Qref + s * (long)ny;
+        // ---- phase 0: zero the planes, (re)build the tables ----
+        __syncthreads();                                          // previous tile's walk is done with the planes / union
+        {
+            uint4* z = reinterpret_cast<uint4*>(smem + L.farS);
+            const int n16 = (ny + 1) * LC_TC;
+            for (int k = tid; k < n16; k += LC_NT) z[k] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        fc = __ldg(&fp->c);
+        const double fsS = __ldg(&fp->sS), fsV = __ldg(&fp->sV), fiS = __ldg(&fp->iS);
+        fiV = __ldg(&fp->iV);
+        for (int j = tid; j < ny + 2; j += LC_NT) {
+            if (j >= ny) { ta[j] = (TT)CUDART_INF; tb[j] = (TT)CUDART_INF; continue; }    // probes may look one past the end
+            const double Qj = sg * Qg[j], w = __ldg(ww_row + j);
+            ta[j] = lc_thr(Qj, true, TT()); tb[j] = lc_thr(Qj, false, TT());
+            wrow[j] = (w == w) ? __dmul_rn(w, -fsV) : 0.0;                  // a NaN weight deposits nothing
+            if (fresh) nxs[j] = (w == w) ? fx_rn(__dmul_rn(w, -fsS)) : 0ll;
+        }
+        for (int k = tid; k < FX_LUT; k += LC_NT) lut[k] = __ldg(lutg + (size_t)sl * FX_LUT + k);
+        {
+            const double qmin = sg * Qg[0], qmax = sg * Qg[ny - 1];
+            qminf = (float)qmin;
+            scalef = (qmax > qmin) ? (float)((double)FX_LUT / (qmax - qmin)) : 0.0f;
+        }
+        __syncthreads();
+
+        // ---- phase 1: scatter -- one deposit of -X per accumulator at the far end of each cell's range ----
+        const int i = tx * LC_TC + c;
+        const bool col_ok = i < nx;
+        long long NVr[LC_U];                                      // -X_V of the thread's cells
+        long long ownS = 0;
+        {
+            const QT* qp = q + (s * (long)ny + r0) * nx + (col_ok ? i : 0);
+#pragma unroll
+            for (int u0 = 0; u0 < LC_U; u0 += LC_U / 2) {          // two batches of loads: fewer live registers
+                QT qv[LC_U / 2];
+#pragma unroll
+                for (int k = 0; k < LC_U / 2; ++k) {
+                    qv[k] = (col_ok && r0 + u0 + k < r1) ? __ldg(qp) : (QT)CUDART_NAN;
+                    qp += nx;
+                }
+#pragma unroll
+                for (int k = 0; k < LC_U / 2; ++k) {
+                    // every lane runs the whole body (the vote below is warp-wide); lanes without a cell -- past the
+                    // last column, or the 12th row of an 11-row segment -- carry NaN and skip only the deposits
+                    const int u = u0 + k, jp = r0 + u;
+                    const bool live = col_ok && jp < r1;
+                    const TT vt = INC ? (TT)qv[k] : -(TT)qv[k];
+                    const double v = (double)vt;
+                    const float vf = (float)vt;
+                    double wn; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(wn) : "r"(wrow_r0 + (live ? u * 8 : 0)));
+                    const long long NV = live ? fx_rn(__dmul_rn(__dsub_rn(v, fc), wn)) : 0ll;      // NaN -> 0
+                    const uint32_t pk = lut[fx_bucket(vf, qminf, scalef)];
+                    const int x0 = (int)(pk & 0xffffu), cnt = (int)(pk >> 16) - x0;
+                    const TT t0 = ta[x0], t1 = ta[x0 + 1];
+                    int x = x0 + ((cnt > 0 && t0 <= vt) ? 1 : 0) + ((cnt > 1 && t1 <= vt) ? 1 : 0);    // #{Q < v}
+                    int h = x;                                                                           // #{Q <= v}
+                    const bool odd = live && (cnt > 2 || tb[x] <= vt);       // denser bucket, or an exact tie
+                    if (__any_sync(XC_FULL, odd)) {
+                        if (odd) {
+                            x = x0; int e = x0 + cnt;
+                            while (x < e) { const int mid = (x + e) >> 1; if (ta[mid] <= vt) x = mid + 1; else e = mid; }
+                            h = x;
+                            while (h < ny && tb[h] <= vt) ++h;
+                        }
+                    }
+                    int target = (x > jp + 1 && use_t1) ? x : ((h <= jp && use_t2) ? h : jp + 1);
+                    if (!(vt == vt)) target = jp + 1;                        // NaN cell: cancels at its own slot
+                    NVr[u] = NV;
+                    if (live) {
+                        const long long NS = lc_lds64(nxs_r0 + u * 8);
+                        const uint32_t off = (uint32_t)target * (LC_TC * 8);
+                        lc_add64(farS_c + off, NS);
+                        lc_add64(farV_c + off, NV);
+                        ownS -= NS;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 2: segment totals, block scan over the 64 segments of every (accumulator, column) ----
+        {
+            long long aS = ownS, aV = 0;
+#pragma unroll
+            for (int u = 0; u < LC_U; ++u) {
+                aV -= NVr[u];                                             // own deposits: +X at slot jp + 1
+                if (r0 + u < r1) { aS += lc_lds64(colS + u * (LC_TC * 8)); aV += lc_lds64(colV + u * (LC_TC * 8)); }
+            }
+            // the union region changes hands here: tables -> totals + Q; every thread is past the scatter phase
+            tot[c * FX_TOTP + seg] = aS;
+            tot[(LC_TC + c) * FX_TOTP + seg] = aV;
+        }
+        for (int j = tid; j < ny; j += LC_NT) qcs[j] = __dmul_rn(__dsub_rn(sg * Qg[j], fc), fiS);
+        __syncthreads();
+        {                                                         // warp = (accumulator, column): exclusive scan over segments
+            long long* row = tot + (size_t)warp * FX_TOTP;
+            const long long a0 = row[2 * lane], a1 = row[2 * lane + 1];
+            long long x = a0 + a1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(XC_FULL, x, o); if (lane >= o) x += t; }
+            const long long ex = x - (a0 + a1);
+            row[2 * lane] = ex; row[2 * lane + 1] = ex + a0;
+        }
+        __syncthreads();
+
+        // ---- phase 3: the walk ----
+        if (col_ok) {
+            long long RS = tot[c * FX_TOTP + seg], RV = tot[(LC_TC + c) * FX_TOTP + seg];
+            double* op = out + (s * (long)ny + r0) * nx + i;
+#pragma unroll
+            for (int u = 0; u < LC_U; ++u) {
+                if (r0 + u >= r1) break;
+                RS += lc_lds64(colS + u * (LC_TC * 8));
+                RV += lc_lds64(colV + u * (LC_TC * 8));
+                double qc; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(qc) : "r"(qcs_r0 + u * 8));
+                const double Vj = __dmul_rn(fx_to_double(RV), fiV);
+                *op = sg * (Vj - qc * fx_to_double(RS));
+                op += nx;
+                RS -= lc_lds64(nxs_r0 + u * 8);                           // own deposits of cell r0 + u, at slot r0 + u + 1
+                RV -= NVr[u];
+            }
+        }
+    }
+}
+
 // NaN-skipping (min, max) of every slice in rngC partials (stand-alone xc_lwa; the
 // fused batch already has them from the levels stage) and max |ww|
 template <typename QT>
@@ -1054,17 +1304,25 @@ extern "C" size_t xc_lwa_workspace_bytes(long S)
     return 1024 + (size_t)(S > 0 ? S : 0) * sizeof(int32_t) + lwa_scratch_doubles(S, false) * sizeof(double);
 }
 
-extern "C" int xc_lwa(const void* q, int q_dtype, long S, int n_eq, int n_x,
-                      const double* Qref, const double* ww,
-                      int increase, int part, int variant,
-                      double* out, void* workspace, size_t ws_bytes, void* stream)
+extern "C" int xc_lwa_ex(const void* q, int q_dtype, long S, int n_eq, int n_x,
+                         const double* Qref, const double* ww, const double* ww_row,
+                         int increase, int part, int variant,
+                         double* out, void* workspace, size_t ws_bytes, void* stream)
 {
     XC_REQUIRE(workspace && ws_bytes >= xc_lwa_workspace_bytes(S), "xc_lwa: workspace too small");
     Arena ar(workspace, ws_bytes);
     int32_t* sorted = ar.take<int32_t>((size_t)(S > 0 ? S : 0));
     double* scratch = ar.take<double>(lwa_scratch_doubles(S, false));
     return lwa_impl(q, q_dtype, S, n_eq, n_x, Qref, ww, increase, part, variant, out, sorted,
-                    nullptr, false, nullptr, scratch, stream);
+                    nullptr, false, nullptr, scratch, stream, nullptr, ww_row);
+}
+
+extern "C" int xc_lwa(const void* q, int q_dtype, long S, int n_eq, int n_x,
+                      const double* Qref, const double* ww,
+                      int increase, int part, int variant,
+                      double* out, void* workspace, size_t ws_bytes, void* stream)
+{
+    return xc_lwa_ex(q, q_dtype, S, n_eq, n_x, Qref, ww, nullptr, increase, part, variant, out, workspace, ws_bytes, stream);
 }
 
 // XCB200_LWA_FX=0 selects the fp64 read-modify-write kernel (k_lwa_fast) instead of
@@ -1087,7 +1345,7 @@ int xc::lwa_wmax(const double* ww, long P, double* parts, void* stream)
 int xc::lwa_impl(const void* q, int q_dtype, long S, int n_eq, int n_x, const double* Qref, const double* ww,
                  int increase, int part, int variant, double* out, int32_t* sorted,
                  int32_t* any_unsorted, bool flags_ready, const double* minmax, double* scratch, void* stream,
-                 const double* wmax_ready)
+                 const double* wmax_ready, const double* ww_row)
 {
     XC_REQUIRE(q && Qref && ww && out, "xc_lwa: null pointer");
     XC_REQUIRE(S > 0 && n_eq >= 1 && n_x >= 1, "xc_lwa: need S>0, n_eq>=1, n_x>=1");
@@ -1150,6 +1408,24 @@ int xc::lwa_impl(const void* q, int q_dtype, long S, int n_eq, int n_x, const do
                                                                rng, rngC, wparts, LWA_WMAX_N, fxs, lutg);
             XC_LAUNCH_OK();
             int rc;
+            // row-constant weights: the column-tile kernel with register-resident own deposits
+            static const char* no_cols = getenv("XCB200_NO_LWA_COLS");
+            const size_t cols_smem = lwa_cols_layout(n_eq, qbytes).total;
+            if (ww_row && !no_cols && n_eq <= FX_SEG * LC_U && n_eq >= 2 && cols_smem <= 227 * 1024) {
+                const long tiles = ns * ((n_x + LC_TC - 1) / LC_TC);
+                const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
+                auto go = [&](auto kern, auto qptr) -> int {
+                    XC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_smem));
+                    kern<<<grid, LC_NT, cols_smem, st>>>(qptr, s0, (int)ns, n_eq, n_x, Qref, ww_row, part, sorted, fxs, lutg, out);
+                    return 0;
+                };
+                int rcc;
+                if (q_dtype == XC_F32) rcc = increase ? go(k_lwa_cols<float, true>, (const float*)q) : go(k_lwa_cols<float, false>, (const float*)q);
+                else                   rcc = increase ? go(k_lwa_cols<double, true>, (const double*)q) : go(k_lwa_cols<double, false>, (const double*)q);
+                if (rcc) return rcc;
+                XC_LAUNCH_OK();
+                continue;
+            }
             if (q_dtype == XC_F32) rc = fx_tc == 16 ? launch(k_lwa_fx<float, 16>, 16, s0, ns) : launch(k_lwa_fx<float, 8>, 8, s0, ns);
             else                   rc = fx_tc == 16 ? launch(k_lwa_fx<double, 16>, 16, s0, ns) : launch(k_lwa_fx<double, 8>, 8, s0, ns);
             if (rc) return rc;

@@ -157,6 +157,36 @@ def gradient_wrt_area(var, var_kind, area, area_kind):
     return out
 
 
+def gradient_coefficients(coord):
+    """NumPy's own np.gradient(edge_order=1) difference coefficients for a 1-D coordinate, in the coordinate's
+    dtype (numpy/lib/_function_base_impl.py): -> (coef fp64 device tensor, uniform flag, holds-fp32 flag)."""
+    x = np.asanyarray(coord)
+    if np.issubdtype(x.dtype, np.integer):
+        x = x.astype(np.float64)
+    d = np.diff(x)
+    if (d == d[0]).all():
+        coef = np.array([2. * d[0], d[0]])
+        uniform = 1
+    else:
+        dx1, dx2 = d[0:-1], d[1:]
+        coef = np.concatenate([-(dx2) / (dx1 * (dx1 + dx2)), (dx2 - dx1) / (dx1 * dx2), dx1 / (dx2 * (dx1 + dx2)),
+                               d[:1], d[-1:]])
+        uniform = 0
+    return to_dev(np.ascontiguousarray(coef, dtype=np.float64)), uniform, int(coef.dtype == np.float32)
+
+
+def gradient_wrt_area_coord(var, var_coord, area, area_coord):
+    """np.gradient(var, var_coord) / np.gradient(area, area_coord) along the last axis of [S, N] fp32/fp64 tensors."""
+    lib = require_cuda()
+    S, N = var.shape
+    out = torch.empty((S, N), dtype=torch.float64, device=var.device)
+    vc, vu, v32 = gradient_coefficients(var_coord)
+    ac, au, a32 = gradient_coefficients(area_coord)
+    check(lib.xc_gradient_wrt_area_coord(_p(var), fdtype(var), _p(vc), vu, v32, _p(area), fdtype(area), _p(ac), au, a32,
+                                         S, N, _p(out), stream_ptr()))
+    return out
+
+
 def leq2(dgrdSdA, dqdA):
     lib = require_cuda()
     out = torch.empty_like(dgrdSdA)
@@ -196,8 +226,18 @@ def lwa_weights(dA):
     return ww
 
 
-def lwa(q, Q, ww, increase, part="all", variant=1, out=None):
-    """q[S, n_eq, n_x], Q[S, n_eq] fp64, ww[n_eq*n_x] fp64 -> LWA[S, n_eq, n_x] fp64."""
+def row_constant(w, ny, nx):
+    """w[ny*nx] on the device -> its first column [ny] (fp64) when every row holds one value (NaN rows
+    included), else None.  One reduction + one host sync; callers do it once per weight array."""
+    m = w.reshape(ny, nx)
+    first = m[:, :1]
+    same = (m == first) | (m.isnan() & first.isnan())
+    return first.reshape(ny).to(torch.float64).contiguous() if bool(same.all()) else None
+
+
+def lwa(q, Q, ww, increase, part="all", variant=1, out=None, ww_row=None):
+    """q[S, n_eq, n_x], Q[S, n_eq] fp64, ww[n_eq*n_x] fp64 -> LWA[S, n_eq, n_x] fp64.
+    ww_row: row_constant(ww, n_eq, n_x) when known (selects the column-tile kernel)."""
     lib = require_cuda()
     if part not in PART:
         raise Exception("invalid part, should be in ['all', 'upper', 'lower']")
@@ -206,8 +246,8 @@ def lwa(q, Q, ww, increase, part="all", variant=1, out=None):
         out = torch.empty((S, ny, nx), dtype=torch.float64, device=q.device)
     nb = lib.xc_lwa_workspace_bytes(S)
     ws = workspace(nb)
-    check(lib.xc_lwa(_p(q), fdtype(q), S, ny, nx, _p(Q), _p(ww), int(bool(increase)), PART[part],
-                     int(variant), _p(out), _p(ws), nb, stream_ptr()))
+    check(lib.xc_lwa_ex(_p(q), fdtype(q), S, ny, nx, _p(Q), _p(ww), _p(ww_row), int(bool(increase)), PART[part],
+                        int(variant), _p(out), _p(ws), nb, stream_ptr()))
     return out
 
 

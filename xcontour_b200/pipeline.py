@@ -31,6 +31,11 @@ from ._lib import KeffLwaArgs, PART, SCAN_PREFIX, SCAN_TOTAL_MINUS, XC_F32, XC_F
 CONTOUR_VARS = ("ctr", "area", "intgrdS", "latEq", "Lmin", "dintSdA", "dqdA", "Leq2", "nkeff")
 
 
+class Outputs(dict):
+    """{name: device tensor} of one batch; ``packed`` is the [9, S, N] buffer the contour-space entries are slabs of."""
+    packed = None
+
+
 def slice_range(S, rank, world):
     """Contiguous block of ceil(S/world) slice indices owned by ``rank``."""
     per = (S + world - 1) // world
@@ -60,6 +65,7 @@ class KeffLwaPlan(object):
         dA = np.ascontiguousarray(np.broadcast_to(np.asarray(dA), (self.ny, self.nx)))
         self.dA = ops.to_dev(dA)
         self.ww = ops.lwa_weights(self.dA.reshape(-1))
+        self.ww_row = ops.row_constant(self.ww, self.ny, self.nx)
         # A(Yeq) table exactly as Contour2D.cal_area_eqCoord_table_hist builds it
         fdt = lat.dtype if lat.dtype in (np.float32, np.float64) else np.float64
         ctrVar = np.ascontiguousarray(np.broadcast_to(lat.astype(fdt)[:, None], (self.ny, self.nx)))
@@ -93,8 +99,13 @@ class KeffLwaPlan(object):
         return _lib.load().xc_keff_lwa_batch_workspace_bytes(S, self.ny, self.nx, self.N)
 
     def alloc_outputs(self, S, lwa=True):
+        """Output tensors of one batch.  The nine contour-space results are slabs of ONE buffer
+        ``out.packed`` [9, S, N] (CONTOUR_VARS order), so that gathering them across ranks is a single
+        collective on a single buffer with no packing copies (ContourGather)."""
         dev = self.dA.device
-        out = {k: torch.empty((S, self.N), dtype=torch.float64, device=dev) for k in CONTOUR_VARS}
+        packed = torch.empty((len(CONTOUR_VARS), S, self.N), dtype=torch.float64, device=dev)
+        out = Outputs((k, packed[i]) for i, k in enumerate(CONTOUR_VARS))
+        out.packed = packed
         out["Qref"] = torch.empty((S, self.ny), dtype=torch.float64, device=dev)
         if lwa:
             out["lwa"] = torch.empty((S, self.ny, self.nx), dtype=torch.float64, device=dev)
@@ -126,11 +137,12 @@ class KeffLwaPlan(object):
         a.cx, a.cy, a.bcx, a.bcy, a.fill_value = self.cx.data_ptr(), self.cy.data_ptr(), self.bcx, self.bcy, self.fill_value
         a.dA_row = self.dA_row.data_ptr() if self.dA_row is not None else None
         a.uniform_dA, a.any_degenerate = int(self.uniform_dA), int(self.any_degenerate)
-        a.ww_row = None
+        a.ww_row = self.ww_row.data_ptr() if self.ww_row is not None else None
         a.table, a.table_coord, a.n_table = self.table.data_ptr(), self.table_coord.data_ptr(), self.ny
         a.eq_coord, a.ww = self.eq_coord.data_ptr(), self.ww.data_ptr()
         a.keff_mask, a.part, a.sub_batch = self.keff_mask, self.part, self.sub_batch
         for k in CONTOUR_VARS:
+            assert k not in out or out[k].is_contiguous()
             setattr(a, k, out[k].data_ptr() if k in out else None)
         a.Qref = out["Qref"].data_ptr() if "Qref" in out else None
         a.lwa = out["lwa"].data_ptr() if "lwa" in out else None
@@ -232,6 +244,54 @@ class HostStreamer(object):
                 ev = torch.cuda.Event()
                 ev.record(self.streams[i])
             pending[i] = (s0, s1, ev)
+
+
+class ContourGather(object):
+    """Asynchronous all-gather of the packed contour-space results ([9, S_local, N] per rank, see
+    KeffLwaPlan.alloc_outputs) on a side stream: the collective of batch b overlaps the kernels of batch b+1.
+    The only communication of the whole path (SURVEY.md §8e); LWA fields stay sharded.  NCCL only (CUDA tensors);
+    every rank contributes the same S_local (the last batch of a run is padded by the caller).
+    ``nbuf`` receive buffers rotate; ``wait()`` makes the current stream wait for every gather in flight."""
+
+    def __init__(self, S_local, N, device, group=None, nbuf=2):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.world = dist.get_world_size(group)
+        self.recv = [torch.empty((self.world, len(CONTOUR_VARS), S_local, N), dtype=torch.float64, device=device)
+                     for _ in range(nbuf)]
+        self.stream = torch.cuda.Stream(device=device)
+        self.done = [None] * nbuf
+        self.n = 0
+
+    def launch(self, packed):
+        """Enqueue the gather of ``packed`` (produced on the current stream); returns the receive buffer
+        [world, 9, S_local, N] it will land in, and the index to pass to ``event()``."""
+        i = self.n % len(self.recv)
+        self.n += 1
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            self.dist.all_gather_into_tensor(self.recv[i].view(-1), packed.view(-1), group=self.group)
+            self.done[i] = torch.cuda.Event()
+            self.done[i].record(self.stream)
+        return self.recv[i], i
+
+    def event(self, i):
+        return self.done[i]
+
+    def wait(self):
+        torch.cuda.current_stream().wait_stream(self.stream)
+
+    @staticmethod
+    def unpack(recv, S_total=None):
+        """[world, 9, S_local, N] -> {name: [world * S_local (or S_total), N]} (views where possible)."""
+        w, k, s, n = recv.shape
+        out = {}
+        for i, name in enumerate(CONTOUR_VARS):
+            t = recv[:, i].reshape(w * s, n)
+            out[name] = t if S_total is None else t[:S_total]
+        return out
 
 
 def gather_contour_space(local, S_total, group=None):
