@@ -355,3 +355,40 @@ def test_gradient_wrt_area_follows_the_contour_coordinate(ops, vort, ldt):
         if not np.allclose(np.diff(levels), np.diff(levels)[0]):
             unit = O.cal_gradient_wrt_area(ctr.values, area.values)
             assert not np.allclose(dq.values[1:-1], unit[1:-1], rtol=1e-3, equal_nan=True)
+
+
+# ---------------------------------------------------------------- the one collective of the path
+def test_contour_gather_nccl_single_rank_roundtrip(ops):
+    """ContourGather (packed [9, S, N] all-gather on a side stream, NCCL) on a one-rank group: what lands in the
+    receive buffer is bit-for-bit what plan.run produced, for two batches in flight; the world-size-2 logic of the
+    dict-based gather is covered on gloo in tests/test_oracle.py."""
+    import os
+    import torch.distributed as dist
+    from xcontour_b200.pipeline import CONTOUR_VARS, ContourGather, KeffLwaPlan
+    lat, lon, q = synth_c4(6, 91, 180)
+    dA = O.latlon_cell_area(lat, lon).astype(np.float32)
+    plan = KeffLwaPlan(lat, lon, dA, 41)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29577")
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", torch.cuda.current_device()))
+    try:
+        g = ContourGather(3, 41, torch.device("cuda", torch.cuda.current_device()), nbuf=2)
+        qd = dev(ops, q)
+        outs = [plan.alloc_outputs(3, lwa=False), plan.alloc_outputs(3, lwa=False)]
+        recvs = []
+        for b in range(2):
+            plan.run(qd[3 * b:3 * b + 3], out=outs[b])
+            recvs.append(g.launch(outs[b].packed)[0])
+        g.wait()
+        torch.cuda.synchronize()
+        for b in range(2):
+            assert recvs[b].shape == (1, len(CONTOUR_VARS), 3, 41)
+            assert torch.equal(recvs[b][0].nan_to_num(), outs[b].packed.nan_to_num())
+            un = ContourGather.unpack(recvs[b])
+            for k in CONTOUR_VARS:
+                assert torch.equal(un[k].nan_to_num(), outs[b][k].nan_to_num())
+    finally:
+        if created:
+            dist.destroy_process_group()

@@ -324,10 +324,10 @@ def test_lwa_fixed_point_hands_infinities_to_the_exact_loop(ops, vort):
 
 
 def test_fixed_point_and_fp64_accumulators_agree(ops):
-    """Cross-check inside the product: the exact integer accumulators (default) and
-    the fp64 read-modify-write kernels (XCB200_LWA_FX=0, XCB200_HIST_FX=0) are two
-    implementations of the same sums; a fresh process with the switches off must
-    reproduce the fused batch within the summation-order tolerance."""
+    """Cross-check inside the product: the exact integer accumulators (default: bin_rows.cu,
+    k_lwa_cols) and the fp64 read-modify-write kernels (XCB200_LWA_FX=0, XCB200_NO_BIN_ROWS=1:
+    k_lwa_fast, k_hist) are two implementations of the same sums; a fresh process with the
+    switches off must reproduce the fused batch within the summation-order tolerance."""
     import subprocess, sys, tempfile
     from conftest import ROOT
     code = (
@@ -344,7 +344,7 @@ def test_fixed_point_and_fp64_accumulators_agree(ops):
         "np.savez(sys.argv[1], **{k: v.cpu().numpy() for k, v in out.items()})\n" % ROOT)
     res = []
     with tempfile.TemporaryDirectory() as td:
-        for i, env in enumerate(({}, {"XCB200_LWA_FX": "0", "XCB200_HIST_FX": "0"})):
+        for i, env in enumerate(({}, {"XCB200_LWA_FX": "0", "XCB200_NO_BIN_ROWS": "1"})):
             f = os.path.join(td, "o%d.npz" % i)
             r = subprocess.run([sys.executable, "-c", code, f], env=dict(os.environ, **env),
                                capture_output=True, text=True, timeout=600)
@@ -841,12 +841,11 @@ def test_contour2d_1d_area_explicit_levels_check_mono(ops, vort):
 
 
 @pytest.mark.parametrize("env", [
-    {"XCB200_LWA_FX": "0"},                                      # fp64 read-modify-write LWA kernel (byte-tag election)
-    {"XCB200_LWA_FX": "0", "XCB200_LWA_HEAVY": "3"},             # ... with register pre-reduction in the scatter
-    {"XCB200_LWA_FX": "0", "XCB200_LWA_DEDUP": "m"},             # ... with the MATCH.ANY peel
-    {"XCB200_HIST_FX": "0"},                                     # warp-private fp64 histograms in the fused Keff pass
-    {"XCB200_HIST_DEDUP": "t", "XCB200_NO_HIST_KEFF": "1"},      # byte tags in the general binning kernel
-    {"XCB200_NO_HIST_KEFF": "1", "XCB200_OVERLAP": "0"},         # general binning kernel, serial schedule
+    {"XCB200_LWA_FX": "0"},                                      # fp64 read-modify-write LWA kernel (k_lwa_fast)
+    {"XCB200_NO_LWA_COLS": "1"},                                 # fixed-point LWA kernel for general weights (k_lwa_fx)
+    {"XCB200_NO_BIN_ROWS": "1"},                                 # general fp64 binning kernel (k_hist) in the fused Keff pass
+    {"XCB200_NO_BIN_ROWS": "1", "XCB200_OVERLAP": "0"},          # ... on the serial schedule
+    {"XCB200_NO_BULK": "1"},                                     # register-staged min/max instead of the bulk-copy ring
     {"XCB200_SUB_BATCH": "1"},                                   # one slice per pass, two passes in flight
 ])
 def test_alternate_code_paths_smoke(ops, env):

@@ -135,6 +135,26 @@ __global__ void __launch_bounds__(256) k_scan_epilogue(const EpiParams p)
     }
 }
 
+// fixed-order reduction of many per-CTA partials ([S][C][2][N] -> [S][1][2][N]) spread over the GPU: with hundreds
+// of partials per slice (config 5: 296 x 2 x 2048 doubles) one CTA per slice would be latency-bound on it
+__global__ void __launch_bounds__(256) k_reduce_partials(const double* __restrict__ part, int C, int N2, double* __restrict__ red)
+{
+    const long s = blockIdx.y;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N2) return;
+    const double* pp = part + (size_t)s * C * N2 + idx;
+    double acc = 0.0; int c = 0;
+    for (; c + 8 <= C; c += 8) {
+        double t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t[u] = __ldg(pp + (size_t)(c + u) * N2);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += t[u];
+    }
+    for (; c < C; ++c) acc += __ldg(pp + (size_t)c * N2);
+    red[(size_t)s * N2 + idx] = acc;
+}
+
 }  // namespace xc
 
 using namespace xc;
@@ -145,8 +165,15 @@ int xc::scan_epilogue(const double* part, int C, long S, int N, int lt, const in
                       const double* eq_coord, int ny, double keff_mask, int increase,
                       double* area, double* intg, double* latEq, double* Lmin, double* dint,
                       double* dq, double* Leq2, double* nkeff, double* Qref,
-                      int32_t* sorted, int32_t* any_unsorted, void* stream)
+                      int32_t* sorted, int32_t* any_unsorted, void* stream, double* reduce_buf)
 {
+    if (reduce_buf && C > 16) {                       // same summation order (c ascending), many CTAs per slice
+        XC_REQUIRE(S <= 65535, "xc_keff_lwa_batch: too many slices per pass");
+        dim3 grid((unsigned)((2 * N + 255) / 256), (unsigned)S);
+        k_reduce_partials<<<grid, 256, 0, (cudaStream_t)stream>>>(part, C, 2 * N, reduce_buf);
+        XC_LAUNCH_OK();
+        part = reduce_buf; C = 1;
+    }
     EpiParams p;
     p.part = part; p.C = C; p.N = N; p.lt = lt; p.decreasing = decreasing;
     p.ctr = ctr; p.ctr_f32 = ctr_f32; p.table = table; p.table_coord = table_coord; p.n_table = n_table;

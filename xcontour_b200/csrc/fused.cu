@@ -77,6 +77,7 @@ FusedPlan fused_plan(long S, int ny, int nx, int N, long sub_req)
     t += 2 * align_up((size_t)p.sub * 4, 256) + 1024;       // decreasing, sorted, flag
     t += 9 * align_up((size_t)p.sub * N * 8, 256);          // contour-space temporaries
     t += align_up((size_t)p.sub * ny * 8, 256);             // Qref
+    t += align_up((size_t)p.sub * 2 * N * 8, 256);          // reduced partials (many CTAs per slice)
     t += align_up((size_t)p.sub * 16, 256) + align_up(lwa_scratch_doubles(p.sub, true) * 8, 256);   // (min, max), LWA scratch
     t *= XC_LANES;                                          // passes in flight (one per internal stream)
     t += 2 * align_up((size_t)ny * 8, 256);                 // row metrics
@@ -114,7 +115,7 @@ extern "C" int xc_keff_lwa_batch(const xc_keff_lwa_args* a, void* workspace, siz
     Arena ar(workspace, ws_bytes);
     struct Lane {
         char *w_minmax, *w_hist; int32_t *sorted, *any_unsorted, *decr; double *edges, *minmax, *lwa_scratch;
-        double *t_ctr, *t_area, *t_intg, *t_latEq, *t_Lmin, *t_dint, *t_dq, *t_Leq2, *t_nk, *t_Q;
+        double *t_ctr, *t_area, *t_intg, *t_latEq, *t_Lmin, *t_dint, *t_dq, *t_Leq2, *t_nk, *t_Q, *t_red;
     } lanes[XC_LANES];
     for (Lane& L : lanes) {
         L.w_minmax = ar.take<char>(pl.ws_minmax);
@@ -130,6 +131,7 @@ extern "C" int xc_keff_lwa_batch(const xc_keff_lwa_args* a, void* workspace, siz
         L.t_Lmin = ar.take<double>((size_t)pl.sub * N);  L.t_dint = ar.take<double>((size_t)pl.sub * N);
         L.t_dq = ar.take<double>((size_t)pl.sub * N);    L.t_Leq2 = ar.take<double>((size_t)pl.sub * N);
         L.t_nk = ar.take<double>((size_t)pl.sub * N);    L.t_Q = ar.take<double>((size_t)pl.sub * ny);
+        L.t_red = ar.take<double>((size_t)pl.sub * 2 * N);
     }
     double* rcos = ar.take<double>((size_t)ny);
     double* dphi = ar.take<double>((size_t)ny);
@@ -203,7 +205,7 @@ extern "C" int xc_keff_lwa_batch(const xc_keff_lwa_args* a, void* workspace, siz
         // scan + (3) latEq + (5)/(4) Lmin, d/dA, Leq2, nkeff + (3) Q(eq_coord), one launch
         if (scan_epilogue(ho.part, ho.C, ns, N, a->lt, L.decr, ctr, a->ctr_dtype == XC_F32,
                           a->table, a->table_coord, a->n_table, a->eq_coord, ny, a->keff_mask, a->increase,
-                          area, intg, latEq, Lmin, dint, dq, Leq2, nk, Qref, L.sorted, L.any_unsorted, ps)) return 1;
+                          area, intg, latEq, Lmin, dint, dq, Leq2, nk, Qref, L.sorted, L.any_unsorted, ps, L.t_red)) return 1;
         mark(4);
         // (6) LWA
         if (a->lwa)

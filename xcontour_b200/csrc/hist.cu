@@ -16,7 +16,7 @@
 // stores its id into a byte tag of the bin and the lane that reads its own id
 // back owns the bin for the round (XCB200_HIST_DEDUP=t).  Bins too many for
 // private copies (e.g. N = 2048 with two accumulators) fall back to shared copies
-// with CAS atomics.  The fused Keff pass has a specialised kernel in hist_keff.cu.
+// with CAS atomics.  The fused Keff pass has a specialised kernel in bin_rows.cu.
 #include "common.cuh"
 #include "internal.h"
 #include "grad2.cuh"
@@ -553,12 +553,6 @@ int xc::bin_accumulate_impl(const void* q, int q_dtype, long S, long P,
     const bool plain_latlon = stencil && stencil->bcx == XC_BC_PERIODIC && stencil->bcy == XC_BC_EXTEND;
     XC_REQUIRE(!stencil || plain_latlon, "xc_bin_accumulate: ghost-cell rules other than (periodic, extend) need an fp32 "
                "tracer with nx %% 4 == 0 and cell areas that are constant along x (dA_row)");
-    if (hist_only && plain_latlon && acc_area && n_int == 0 && !q_mask && !bin_idx && !closed_right &&
-        edges_stride == N + 1 && pl.priv) {
-        const int r = hist_keff_try(q, q_dtype, S, P, edges, N, dA, dA_dtype, stencil, pl.C, hp.part, stream);
-        if (r == 2) return 1;
-        if (r == 0) { hist_only->part = hp.part; hist_only->C = pl.C; return 0; }
-    }
     for (long s0 = 0; s0 < S; s0 += 65535) {
         long ns = S - s0 < 65535 ? S - s0 : 65535;
         hp.s0 = s0;

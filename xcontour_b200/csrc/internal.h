@@ -47,12 +47,7 @@ int scan_epilogue(const double* part, int C, long S, int N, int lt, const int32_
                   const double* eq_coord, int ny, double keff_mask, int increase,
                   double* area, double* intg, double* latEq, double* Lmin, double* dint,
                   double* dq, double* Leq2, double* nkeff, double* Qref,
-                  int32_t* sorted, int32_t* any_unsorted, void* stream);
-
-// dedicated fused-Keff binning kernel (hist_keff.cu): 0 launched, 1 not applicable, 2 error
-int hist_keff_try(const void* q, int q_dtype, long S, long P, const double* edges, int N,
-                  const void* dA, int dA_dtype, const StencilArgs* st, int C,
-                  double* part, void* stream);
+                  int32_t* sorted, int32_t* any_unsorted, void* stream, double* reduce_buf = nullptr);
 
 // row-march fused-Keff binning kernel (bin_rows.cu): 0 launched (*C_out CTAs per slice), 1 not applicable, 2 error
 int bin_rows_try(const void* q, int q_dtype, long S, const double* edges, int N,

@@ -52,18 +52,6 @@ __global__ void k_check_sorted(const double* __restrict__ Q, int ny, int increas
 #ifndef XC_LWA_NI
 #define XC_LWA_NI 3
 #endif
-#ifndef XC_LWA_MAP           /* 1: lane l owns rows NI*l+u of a block; 0: rows 32*u+l */
-#define XC_LWA_MAP 1
-#endif
-#ifndef XC_LWA_UPFRONT       /* 1: all MATCH.ANY of a step issued before the peel loops */
-#define XC_LWA_UPFRONT 0
-#endif
-#ifndef XC_LWA_MINB          /* min blocks per SM given to __launch_bounds__ (0 = unspecified) */
-#define XC_LWA_MINB 1
-#endif
-#ifndef XC_LWA_BISECT        /* unrolled branch-free bisection steps before the fallback loop */
-#define XC_LWA_BISECT 0
-#endif
 constexpr int LWA_NI  = XC_LWA_NI;
 constexpr int LWA_BIG = 32 * LWA_NI;       // rows per staged block
 // staging strides chosen so that the transposed store [col][row] of a 2-row x 16-col
@@ -131,22 +119,10 @@ __device__ __forceinline__ void lwa_scatter(double2* Dw, uint8_t* tagw, const in
                                             const bool (&act)[LWA_NI], int lane)
 {
     if (MATCH) {
-#if XC_LWA_UPFRONT
-        unsigned peers[LWA_NI];
 #pragma unroll
         for (int u = 0; u < LWA_NI; ++u) {
-            peers[u] = __match_any_sync(XC_FULL, act[u] ? (unsigned)target[u] : (0x80000000u | (unsigned)lane));
-            if (!act[u]) peers[u] = 0u;
-        }
-#endif
-#pragma unroll
-        for (int u = 0; u < LWA_NI; ++u) {
-#if XC_LWA_UPFRONT
-            unsigned pr = peers[u];
-#else
             unsigned pr = __match_any_sync(XC_FULL, act[u] ? (unsigned)target[u] : (0x80000000u | (unsigned)lane));
             if (!act[u]) pr = 0u;
-#endif
             do {
                 if (pr && (__ffs(pr) - 1) == lane) {
                     double2 t = Dw[target[u]]; t.x += nw[u]; t.y += nwv[u]; Dw[target[u]] = t;
@@ -176,16 +152,8 @@ __device__ __forceinline__ void lwa_scatter(double2* Dw, uint8_t* tagw, const in
 }
 
 // grid = (ceil(nx/TC), nslices), block = TC warps; warp w owns column i0 + w.
-#if XC_LWA_MINB > 0
-#define XC_LWA_BOUNDS __launch_bounds__(LWA_MAX_TC * 32, XC_LWA_MINB)
-#else
-#define XC_LWA_BOUNDS __launch_bounds__(LWA_MAX_TC * 32)
-#endif
-#if XC_LWA_MAP
+#define XC_LWA_BOUNDS __launch_bounds__(LWA_MAX_TC * 32, 1)
 #define LWA_ROW(lane, u) (LWA_NI * (lane) + (u))
-#else
-#define LWA_ROW(lane, u) (32 * (u) + (lane))
-#endif
 
 template <typename QT, bool MATCH, int HEAVY>
 __global__ void XC_LWA_BOUNDS
@@ -287,14 +255,6 @@ k_lwa_fast(const QT* __restrict__ q, long s0, int ny, int nx,
                 const uint32_t pk = lut[lwa_bucket((float)v, qminf, scalef)];
                 int x = (int)(pk & 0xffffu), e = (int)(pk >> 16);
                 const int e0 = e;                            // end of v's bucket: rows >= e0 have Q > v
-#pragma unroll
-                for (int it = 0; it < XC_LWA_BISECT; ++it) { // branch-free bisection: 3 steps cover e - x <= 7
-                    const int mid = (x + e) >> 1;
-                    const bool open = x < e;
-                    const bool below = open && (Qs[open ? mid : 0] < v);
-                    x = below ? mid + 1 : x;
-                    e = (open && !below) ? mid : e;
-                }
                 while (x < e) {                              // wide buckets (flat stretches of Q)
                     const int mid = (x + e) >> 1;
                     if (Qs[mid] < v) x = mid + 1; else e = mid;
@@ -377,19 +337,10 @@ k_lwa_fast(const QT* __restrict__ q, long s0, int ny, int nx,
 // Two tile shapes: 16 columns x 1024 threads (one CTA per SM; a warp-wide global
 // access then covers 2 rows x 64/128 B instead of 4 rows x 32/64 B, which is what
 // the LSU data pipe is paid in) while the four planes fit 227 KB, else 8 x 512.
-#ifndef XC_FX_LEAN
-#define XC_FX_LEAN 0
-#endif
-#ifndef XC_FX_PAIR           /* 1: the lo and hi word of an accumulator sit next to each other ([slot][column][lo,hi]), so
-                                the two prefix passes read one LDS.64 per accumulator and row instead of two LDS.32 and
-                                need no recombination.  A/B switch, not yet timed; the default path is textually
-                                untouched (every use is an #if / #else around the original statement). */
-#define XC_FX_PAIR 0
-#endif
 #ifndef XC_FX_LUT            /* buckets of the LUT over Q.  The bisection that finishes the search is the most
                                 expensive source line of the kernel (9 % of its instructions, ncu source page); 4096
                                 buckets still fit the 16-column tile at ny = 721 (224 of 227 KB).  Not yet timed. */
-#define XC_FX_LUT 2048
+#define XC_FX_LUT 4096
 #endif
 constexpr int FX_SEG = 64;                 // row segments per column (threads = FX_SEG * TC)
 constexpr int FX_LUT = XC_FX_LUT;
@@ -429,12 +380,8 @@ __device__ __forceinline__ void fx_add64(uint32_t* lo, uint32_t* hi, int idx, lo
 {
     const uint32_t xl = (uint32_t)x, xh = (uint32_t)((unsigned long long)x >> 32);
     const uint32_t old = atomicAdd(lo + idx, xl);
-#if XC_FX_LEAN               /* carry from a 64-bit add (IADD3 + carry-out) instead of a comparison; prepared, not yet timed */
-    atomicAdd(hi + idx, xh + (uint32_t)(((unsigned long long)old + xl) >> 32));
-#else
     const uint32_t carry = (uint32_t)((old + xl) < xl);
     atomicAdd(hi + idx, xh + carry);
-#endif
 }
 
 // Per-slice preparation (one CTA per slice): the fixed-point scales from the
@@ -518,16 +465,6 @@ __device__ __forceinline__ void fx_value(double qraw, float, double sg, double& 
 #ifndef XC_FX_PROBES
 #define XC_FX_PROBES 2
 #endif
-#ifndef XC_FX_EXP            /* timing-split builds only (results wrong by construction): 1 = scatter phase without
-                                its shared-memory atomics, 2 = no scatter phase at all (scripts/lwa_split.sh) */
-#define XC_FX_EXP 0
-#endif
-#ifndef XC_FX_OWN            /* 1: the +X deposit at the cell's own slot is made with shared-memory atomics in the
-                                scatter phase instead of being re-derived from (q, ww) in the prefix phase.  Measured
-                                split (profiles/r1_time_split.txt): the four atomics of a cell cost 5 % of the kernel,
-                                the prefix side 64 % -- candidate for round 2, not yet timed (scripts/ab_round2.sh). */
-#define XC_FX_OWN 0
-#endif
 constexpr int FX_U = XC_FX_U;        // rows whose loads are in flight together
 
 template <typename QT, int FX_TC>
@@ -580,15 +517,11 @@ k_lwa_fx(const QT* __restrict__ q, long s0, long sbase, int ny, int nx,
     const int r0 = (int)(((long)seg * ny) / FX_SEG), r1 = (int)(((long)(seg + 1) * ny) / FX_SEG);
     const QT* qc = q + (s * (long)ny + r0) * nx + i;
     const double* wc = ww + (long)r0 * nx + i;
-#if XC_FX_PAIR
-    uint32_t* fcol = far + 2 * c;                              // S: fcol[t * 2 FX_TC + {0, 1}], V: 2 * plane further on
-#else
     uint32_t* fcol = far + c;                                  // word (slot t, plane k) = fcol[t * FX_TC + k * plane]
-#endif
 
     // ---- scatter: one deposit of -X at the far end of each cell's range ----
     long long ownS = 0, ownV = 0;
-    if (col_ok && XC_FX_EXP != 2) {
+    if (col_ok) {
         const double nsS = -fsS, nsV = -fsV;
         const QT* qp = qc; const double* wp = wc;
         for (int jb = r0; jb < r1; jb += FX_U) {
@@ -623,35 +556,10 @@ k_lwa_fx(const QT* __restrict__ q, long s0, long sbase, int ny, int nx,
                     }
                     if (h <= jp && use_t2) target = h;
                 }
-#if XC_FX_OWN
-                if (target == jp + 1) continue;                  // inactive: nothing to deposit
-                {
-#if XC_FX_PAIR
-                    uint32_t* so = fcol + (jp + 1) * 2 * FX_TC;  // +X at the own slot
-                    fx_add64(so, so + 1, 0, -NS);
-                    fx_add64(so + 2 * plane, so + 2 * plane + 1, 0, -NV);
-#else
-                    uint32_t* so = fcol + (jp + 1) * FX_TC;      // +X at the own slot
-                    fx_add64(so, so + plane, 0, -NS);
-                    fx_add64(so + 2 * plane, so + 3 * plane, 0, -NV);
-#endif
-                }
-#else
                 ownS -= NS; ownV -= NV;
-#endif
-#if XC_FX_PAIR
-                uint32_t* slot = fcol + target * 2 * FX_TC;
-                fx_add64(slot, slot + 1, 0, NS);
-                fx_add64(slot + 2 * plane, slot + 2 * plane + 1, 0, NV);
-#else
                 uint32_t* slot = fcol + target * FX_TC;
-#if XC_FX_EXP == 1
-                ownS += (long long)(slot - far);                 // keeps the search alive without touching shared memory
-#else
                 fx_add64(slot, slot + plane, 0, NS);
                 fx_add64(slot + 2 * plane, slot + 3 * plane, 0, NV);
-#endif
-#endif
             }
         }
     }
@@ -660,18 +568,10 @@ k_lwa_fx(const QT* __restrict__ q, long s0, long sbase, int ny, int nx,
     // ---- prefix down the columns: segment totals, block scan, final walk ----
     {
         unsigned long long aSl = 0, aVl = 0; long long aSh = 0, aVh = 0;
-#if XC_FX_PAIR
-        const uint32_t* sl = fcol + r0 * 2 * FX_TC;
-        for (int j = r0; j < r1; ++j, sl += 2 * FX_TC) {          // sums modulo 2^64
-            const uint2 a = *reinterpret_cast<const uint2*>(sl), b = *reinterpret_cast<const uint2*>(sl + 2 * plane);
-            aSl += ((unsigned long long)a.y << 32) | a.x; aVl += ((unsigned long long)b.y << 32) | b.x;
-        }
-#else
         const uint32_t* sl = fcol + r0 * FX_TC;
         for (int j = r0; j < r1; ++j, sl += FX_TC) {
             aSl += sl[0]; aSh += (int32_t)sl[plane]; aVl += sl[2 * plane]; aVh += (int32_t)sl[3 * plane];
         }
-#endif
         tot[c * FX_TOTP + seg] = (long long)aSl + (aSh << 32) + ownS;
         tot[(FX_TC + c) * FX_TOTP + seg] = (long long)aVl + (aVh << 32) + ownV;
     }
@@ -693,26 +593,6 @@ k_lwa_fx(const QT* __restrict__ q, long s0, long sbase, int ny, int nx,
         const QT* qp = qc; const double* wp = wc;
         const uint32_t* sl = fcol + r0 * FX_TC;
         const double* Qj = Qs + r0;
-#if XC_FX_PAIR && !XC_FX_OWN
-#error "XC_FX_PAIR is implemented for the XC_FX_OWN walk only"
-#endif
-#if XC_FX_OWN
-        for (int j = r0; j < r1; ++j) {                          // every deposit is in the planes: a plain inclusive prefix
-#if XC_FX_PAIR
-            const uint32_t* sp = fcol + j * 2 * FX_TC;
-            const uint2 a = *reinterpret_cast<const uint2*>(sp), b = *reinterpret_cast<const uint2*>(sp + 2 * plane);
-            RS += (long long)(((unsigned long long)a.y << 32) | a.x);
-            RV += (long long)(((unsigned long long)b.y << 32) | b.x);
-#else
-            RS += (long long)(((unsigned long long)sl[plane] << 32) | sl[0]);
-            RV += (long long)(((unsigned long long)sl[3 * plane] << 32) | sl[2 * plane]);
-#endif
-            const double Sj = __dmul_rn(fx_to_double(RS), fiS), Vj = __dmul_rn(fx_to_double(RV), fiV);
-            *op = sg * (Vj - (*Qj - fc) * Sj);
-            op += nx; sl += FX_TC; ++Qj;
-        }
-        (void)qc; (void)wc;
-#else
         for (int jb = r0; jb < r1; jb += FX_U) {
             QT qv[FX_U]; double wv[FX_U];
 #pragma unroll
@@ -739,7 +619,6 @@ k_lwa_fx(const QT* __restrict__ q, long s0, long sbase, int ny, int nx,
                 }
             }
         }
-#endif
     }
 }
 
@@ -764,23 +643,23 @@ k_lwa_fx(const QT* __restrict__ q, long s0, long sbase, int ny, int nx,
 //     of a slice are built once per CTA and slice, not once per tile.
 // grid = SM count, block = 1024 = 16 columns x 64 row segments, one CTA per SM.
 constexpr int LC_TC = 16, LC_U = 12, LC_NT = FX_SEG * LC_TC;
-struct LwaColsSmem { size_t farS, farV, nxs, uni, total; size_t lut, ta, tb, wrow, tot, qc; };
+struct LwaColsSmem { size_t farS, farV, nxs, wrow, qc, ta, tb, uni, lut, tot, total; };
 static __host__ __device__ inline LwaColsSmem lwa_cols_layout(int ny, int tbytes)
 {
     LwaColsSmem L; size_t o = 0;
     const size_t plane = (size_t)(ny + 1) * LC_TC * 8;
+    const size_t col8 = (size_t)((ny + 1) & ~1) * 8;
     L.farS = o; o += plane;
     L.farV = o; o += plane;
-    L.nxs = o;  o += (size_t)((ny + 1) & ~1) * 8;
-    L.uni = o;
-    size_t a = 0;                                              // scatter-phase view of the union
-    L.lut = o + a;  a += (size_t)FX_LUT * 4;
-    L.wrow = o + a; a += (size_t)((ny + 1) & ~1) * 8;
-    L.ta = o + a;   a += (size_t)((ny + 2 + 3) & ~3) * tbytes;       // two +inf entries past the end
-    L.tb = o + a;   a += (size_t)((ny + 2 + 3) & ~3) * tbytes;
-    size_t b = 0;                                              // prefix-phase view
-    L.tot = o + b;  b += (size_t)2 * LC_TC * FX_TOTP * 8;
-    L.qc = o + b;   b += (size_t)((ny + 1) & ~1) * 8;
+    // per-slice tables, built when a CTA meets a new slice
+    L.nxs = o;  o += col8;                                     // -rn(w 2^kS)
+    L.wrow = o; o += col8;                                     // -w 2^kV
+    L.qc = o;   o += col8;                                     // (Q_j - c) 2^-kS
+    L.ta = o;   o += (size_t)((ny + 2 + 3) & ~3) * tbytes;     // smallest value > Q_j, two +inf entries past the end
+    L.tb = o;   o += (size_t)((ny + 2 + 3) & ~3) * tbytes;     // smallest value >= Q_j
+    // per tile: the LUT (scatter phase) and the segment totals (prefix phase) share one region
+    L.uni = o; L.lut = o; L.tot = o;
+    const size_t a = (size_t)((FX_LUT + 2 + 7) & ~7) * 2, b = (size_t)2 * LC_TC * FX_TOTP * 8;
     L.total = o + (a > b ? a : b);
     return L;
 }
@@ -831,7 +710,7 @@ k_lwa_cols(const QT* __restrict__ q, long s0, int nslices, int ny, int nx,
     extern __shared__ __align__(16) unsigned char smem[];
     const LwaColsSmem L = lwa_cols_layout(ny, (int)sizeof(TT));
     long long* nxs = reinterpret_cast<long long*>(smem + L.nxs);
-    uint32_t*  lut = reinterpret_cast<uint32_t*>(smem + L.lut);
+    uint16_t*  lut = reinterpret_cast<uint16_t*>(smem + L.lut);
     double*    wrow = reinterpret_cast<double*>(smem + L.wrow);
     TT*        ta = reinterpret_cast<TT*>(smem + L.ta);
     TT*        tb = reinterpret_cast<TT*>(smem + L.tb);
@@ -875,23 +754,30 @@ k_lwa_cols(const QT* __restrict__ q, long s0, int nslices, int ny, int nx,
             const int n16 = (ny + 1) * LC_TC;
             for (int k = tid; k < n16; k += LC_NT) z[k] = make_uint4(0u, 0u, 0u, 0u);
         }
-        fc = __ldg(&fp->c);
-        const double fsS = __ldg(&fp->sS), fsV = __ldg(&fp->sV), fiS = __ldg(&fp->iS);
-        fiV = __ldg(&fp->iV);
-        for (int j = tid; j < ny + 2; j += LC_NT) {
-            if (j >= ny) { ta[j] = (TT)CUDART_INF; tb[j] = (TT)CUDART_INF; continue; }    // probes may look one past the end
-            const double Qj = sg * Qg[j], w = __ldg(ww_row + j);
-            ta[j] = lc_thr(Qj, true, TT()); tb[j] = lc_thr(Qj, false, TT());
-            wrow[j] = (w == w) ? __dmul_rn(w, -fsV) : 0.0;                  // a NaN weight deposits nothing
-            if (fresh) nxs[j] = (w == w) ? fx_rn(__dmul_rn(w, -fsS)) : 0ll;
-        }
-        for (int k = tid; k < FX_LUT; k += LC_NT) lut[k] = __ldg(lutg + (size_t)sl * FX_LUT + k);
-        {
+        if (fresh) {                                              // tables of this slice (shared by all its tiles)
+            fc = __ldg(&fp->c);
+            const double fsS = __ldg(&fp->sS), fsV = __ldg(&fp->sV), fiS = __ldg(&fp->iS);
+            fiV = __ldg(&fp->iV);
+            for (int j = tid; j < ny + 2; j += LC_NT) {
+                if (j >= ny) { ta[j] = (TT)CUDART_INF; tb[j] = (TT)CUDART_INF; continue; }    // probes may look one past the end
+                const double Qj = sg * Qg[j], w = __ldg(ww_row + j);
+                ta[j] = lc_thr(Qj, true, TT()); tb[j] = lc_thr(Qj, false, TT());
+                wrow[j] = (w == w) ? __dmul_rn(w, -fsV) : 0.0;              // a NaN weight deposits nothing
+                nxs[j] = (w == w) ? fx_rn(__dmul_rn(w, -fsS)) : 0ll;
+                qcs[j] = __dmul_rn(__dsub_rn(Qj, fc), fiS);
+            }
             const double qmin = sg * Qg[0], qmax = sg * Qg[ny - 1];
             qminf = (float)qmin;
             scalef = (qmax > qmin) ? (float)((double)FX_LUT / (qmax - qmin)) : 0.0f;
         }
+        // LUT: first row of every bucket (+ the end marker), unpacked from the (first[b], first[b+1]) pairs
+        for (int k = tid; k < FX_LUT; k += LC_NT) {
+            const uint32_t pk = __ldg(lutg + (size_t)sl * FX_LUT + k);
+            lut[k] = (uint16_t)(pk & 0xffffu);
+            if (k == FX_LUT - 1) lut[FX_LUT] = (uint16_t)(pk >> 16);
+        }
         __syncthreads();
+        const TT t_first = ta[0], t_last = ta[ny - 1];            // below / not below every Q: no search
 
         // ---- phase 1: scatter -- one deposit of -X per accumulator at the far end of each cell's range ----
         const int i = tx * LC_TC + c;
@@ -919,8 +805,10 @@ k_lwa_cols(const QT* __restrict__ q, long s0, int nslices, int ny, int nx,
                     const float vf = (float)vt;
                     double wn; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(wn) : "r"(wrow_r0 + (live ? u * 8 : 0)));
                     const long long NV = live ? fx_rn(__dmul_rn(__dsub_rn(v, fc), wn)) : 0ll;      // NaN -> 0
-                    const uint32_t pk = lut[fx_bucket(vf, qminf, scalef)];
-                    const int x0 = (int)(pk & 0xffffu), cnt = (int)(pk >> 16) - x0;
+                    const int bk = fx_bucket(vf, qminf, scalef);
+                    int x0 = (int)lut[bk], cnt = (int)lut[bk + 1] - x0;
+                    if (vt >= t_last) { x0 = ny; cnt = 0; }                  // above every Q (the end buckets are the dense ones)
+                    if (vt < t_first) { x0 = 0; cnt = 0; }
                     const TT t0 = ta[x0], t1 = ta[x0 + 1];
                     int x = x0 + ((cnt > 0 && t0 <= vt) ? 1 : 0) + ((cnt > 1 && t1 <= vt) ? 1 : 0);    // #{Q < v}
                     int h = x;                                                                           // #{Q <= v}
@@ -956,11 +844,10 @@ k_lwa_cols(const QT* __restrict__ q, long s0, int nslices, int ny, int nx,
                 aV -= NVr[u];                                             // own deposits: +X at slot jp + 1
                 if (r0 + u < r1) { aS += lc_lds64(colS + u * (LC_TC * 8)); aV += lc_lds64(colV + u * (LC_TC * 8)); }
             }
-            // the union region changes hands here: tables -> totals + Q; every thread is past the scatter phase
+            // the shared region changes hands here: LUT -> totals; every thread is past the scatter phase
             tot[c * FX_TOTP + seg] = aS;
             tot[(LC_TC + c) * FX_TOTP + seg] = aV;
         }
-        for (int j = tid; j < ny; j += LC_NT) qcs[j] = __dmul_rn(__dsub_rn(sg * Qg[j], fc), fiS);
         __syncthreads();
         {                                                         // warp = (accumulator, column): exclusive scan over segments
             long long* row = tot + (size_t)warp * FX_TOTP;
@@ -1357,12 +1244,7 @@ int xc::lwa_impl(const void* q, int q_dtype, long S, int n_eq, int n_x, const do
     const bool match = lwa_use_match();
     const int qbytes = q_dtype == XC_F32 ? 4 : 8;
     const int tc = (n_eq < 65535) ? lwa_pick_tc(n_eq, qbytes, !match) : 0;
-#ifndef XC_FX_TC8            /* 1: always the 8-column / 512-thread tile (two CTAs per SM overlap each other's barriers);
-                                with XC_FX_OWN the walk has no global loads left, which is what made 16 columns pay.
-                                A/B switch, not yet timed. */
-#define XC_FX_TC8 0
-#endif
-    const int fx_tc = (!XC_FX_TC8 && lwa_fx_layout(n_eq, 16).total <= 227 * 1024) ? 16 : 8;
+    const int fx_tc = lwa_fx_layout(n_eq, 16).total <= 227 * 1024 ? 16 : 8;
     const LwaFxSmem FL = lwa_fx_layout(n_eq, fx_tc);
     const bool fx = (variant == 1) && lwa_use_fx() && scratch && n_eq < 65535 && FL.total <= 227 * 1024;
     const bool fast = fx || ((variant == 1) && tc >= 1 && (size_t)tc * (n_eq + 2) * 16 >= (size_t)(LWA_LUT + 1) * 2);
