@@ -271,6 +271,9 @@ typedef struct xc_keff_lwa_args {
      * ww_row [n_y] fp64: ww of every row when the LWA weights are constant along x. */
     const double* dA_row;     int uniform_dA;  int any_degenerate;
     const double* ww_row;
+    /* opt-in, NOT a drop-in result: lwa points to [S][n_y][n_x] fp32 and receives the fp64 result rounded once
+     * (halves the bytes of the largest output; needs ww_row and n_y <= 768) */
+    int           lwa_f32;
 } xc_keff_lwa_args;
 #define XC_N_STAGES 5
 

@@ -392,3 +392,21 @@ def test_contour_gather_nccl_single_rank_roundtrip(ops):
     finally:
         if created:
             dist.destroy_process_group()
+
+
+def test_lwa_f32_opt_in_is_the_fp64_field_rounded_once(ops):
+    """alloc_outputs(lwa_dtype=float32) (opt-in, documented as not a drop-in): the field equals the fp64 result
+    cast to fp32, bit for bit; everything else is unchanged."""
+    from xcontour_b200.pipeline import KeffLwaPlan
+    lat, lon, q = synth_c4(3, 181, 360)
+    dA = O.latlon_cell_area(lat, lon).astype(np.float32)
+    plan = KeffLwaPlan(lat, lon, dA, 91)
+    qd = dev(ops, q)
+    a = plan.run(qd)
+    b = plan.run(qd, out=plan.alloc_outputs(3, lwa_dtype=torch.float32))
+    torch.cuda.synchronize()
+    assert b["lwa"].dtype == torch.float32
+    assert torch.equal(b["lwa"], a["lwa"].to(torch.float32))
+    for k in a:
+        if k != "lwa":
+            assert torch.equal(a[k].nan_to_num(), b[k].nan_to_num()), k

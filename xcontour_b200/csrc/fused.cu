@@ -210,7 +210,8 @@ extern "C" int xc_keff_lwa_batch(const xc_keff_lwa_args* a, void* workspace, siz
         // (6) LWA
         if (a->lwa)
             if (lwa_impl(q, a->q_dtype, ns, ny, nx, Qref, a->ww, a->increase, a->part, 1,
-                         a->lwa + (size_t)s0 * P, L.sorted, L.any_unsorted, true, L.minmax, L.lwa_scratch, ps, wmaxp, a->ww_row)) return 1;
+                         a->lwa_f32 ? reinterpret_cast<double*>(reinterpret_cast<float*>(a->lwa) + (size_t)s0 * P) : a->lwa + (size_t)s0 * P,
+                         L.sorted, L.any_unsorted, true, L.minmax, L.lwa_scratch, ps, wmaxp, a->ww_row, a->lwa_f32)) return 1;
         mark(5);
         ++pass;
     }

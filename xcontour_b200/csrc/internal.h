@@ -70,7 +70,7 @@ size_t lwa_scratch_doubles(long S, bool have_minmax);
 int lwa_impl(const void* q, int q_dtype, long S, int n_eq, int n_x, const double* Qref, const double* ww,
              int increase, int part, int variant, double* out, int32_t* sorted,
              int32_t* any_unsorted, bool flags_ready, const double* minmax, double* scratch, void* stream,
-             const double* wmax_ready = nullptr, const double* ww_row = nullptr);
+             const double* wmax_ready = nullptr, const double* ww_row = nullptr, int out_f32 = 0);
 // partial max |ww| (lwa_wmax_doubles() values) for wmax_ready: the fused batch computes them once per call
 size_t lwa_wmax_doubles();
 int lwa_wmax(const double* ww, long P, double* parts, void* stream);

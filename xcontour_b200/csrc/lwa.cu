@@ -19,9 +19,7 @@
 // Profiles that are not sorted (or contain NaN) take the exact O(n_eq^2) kernel;
 // variant 2 (cal_local_wave_activity2) has its own gather-only kernel.
 // Bound: shared-memory scatter throughput, not HBM (profiles/README.md).
-#include "common.cuh"
-#include "internal.h"
-#include <math_constants.h>
+#include "lwa_fx.cuh"
 #include <stdlib.h>
 
 namespace xc {
@@ -311,575 +309,6 @@ k_lwa_fast(const QT* __restrict__ q, long s0, int ny, int nx,
     }
 }
 
-// ---------------------------------------------------------------------------
-// Fixed-point variant of the fast kernel (default).  Measured on B200
-// (scripts/micro/atoms_bench.cu): a native shared-memory integer atomic
-// (ATOMS.ADD.U32) costs 2.6-3.4 cycles per warp instruction, a 64-bit add built
-// from two of them plus a carry 4.3-5.0, against 15-18.5 for ONE conflict-free
-// read-modify-write round of an fp64 pair (and 2.4 election rounds on average in
-// k_lwa_fast).  So the difference arrays become 64-bit two's-complement integers:
-//     X_S = rn(w * 2^kS),   X_V = rn(w * (v - c) * 2^kV)
-// with c the mid-range of the slice and kS, kV chosen per slice so that a column
-// of n_eq terms cannot overflow 63 bits (|X| < 2^min(51, 62 - ceil(log2(n_eq+1))): 51
-// significant bits at n_eq = 721, i.e. the resolution of the largest term's own
-// fp64 ulp).  Integer adds are exact and order-independent, so
-//   * any thread may deposit into any slot of its column tile: lanes run along
-//     x (coalesced loads, no transposed staging), there is no lane election, no
-//     warp-private array, and a CTA has as many warps as registers allow;
-//   * the +X deposit at slot j'+1 never touches shared memory: the prefix pass
-//     re-derives it from (q, ww) with the same rounding, and an inactive cell
-//     deposits -X at j'+1, which cancels exactly;
-//   * results are bit-reproducible whatever the schedule.
-//   LWA[j] = sg * ( V_j 2^-kV - (Q_j - c) * S_j 2^-kS ).
-// grid = (ceil(n_x / 8), slices); block = FX_NT threads = (column c, row segment).
-// Shared memory: four u32 planes [slot][column] (lo/hi words of S and V), Q, a
-// 1024-bucket LUT over Q and the per-segment totals of the block scan.
-// Two tile shapes: 16 columns x 1024 threads (one CTA per SM; a warp-wide global
-// access then covers 2 rows x 64/128 B instead of 4 rows x 32/64 B, which is what
-// the LSU data pipe is paid in) while the four planes fit 227 KB, else 8 x 512.
-#ifndef XC_FX_LUT            /* buckets of the LUT over Q.  The bisection that finishes the search is the most
-                                expensive source line of the kernel (9 % of its instructions, ncu source page); 4096
-                                buckets still fit the 16-column tile at ny = 721 (224 of 227 KB).  Not yet timed. */
-#define XC_FX_LUT 4096
-#endif
-constexpr int FX_SEG = 64;                 // row segments per column (threads = FX_SEG * TC)
-constexpr int FX_LUT = XC_FX_LUT;
-constexpr int FX_TOTP = FX_SEG + 2;        // padded row of the totals table
-
-struct LwaFxSmem { size_t off_Q, off_far, off_lut, off_tot, total; int plane; };
-static __host__ __device__ inline LwaFxSmem lwa_fx_layout(int ny, int FX_TC)
-{
-    LwaFxSmem L;
-    L.plane = ((ny + 1) * FX_TC + 3) & ~3;                       // u32 words per plane
-    size_t o = 0;
-    L.off_Q = o;   o += (size_t)((ny + 1) & ~1) * 8;
-    L.off_far = o; o += (size_t)4 * L.plane * 4;
-    L.off_lut = o; o += (size_t)FX_LUT * 4;
-    L.off_tot = o; o += (size_t)2 * FX_TC * FX_TOTP * 8;
-    L.total = o;
-    return L;
-}
-
-// (Conversions: F2I / I2F with a 64-bit side cost ~2.3 cycles per warp instruction on
-// the XU pipe, scripts/micro/cvt_bench.cu; the magic-number forms on the fp64 / integer
-// pipes measure the same or worse and cost issue slots, which is what this kernel is
-// short of, so the hardware conversions stay.)
-__device__ __forceinline__ int fx_bucket(float vf, float qminf, float scalef)
-{
-    const float t = fminf(fmaxf((vf - qminf) * scalef, 0.0f), (float)(FX_LUT - 1));
-    return __float2int_rz(t);
-}
-__device__ __forceinline__ long long fx_rn(double x) { return __double2ll_rn(x); }
-__device__ __forceinline__ double fx_to_double(long long r) { return (double)r; }
-
-// 64-bit two's-complement add into (lo[idx], hi[idx]) with two native 32-bit
-// shared atomics; the carry out of the low word is decided by the value the low
-// word held when THIS add reached it, so the pair ends up as the exact sum modulo
-// 2^64 in any interleaving.
-__device__ __forceinline__ void fx_add64(uint32_t* lo, uint32_t* hi, int idx, long long x)
-{
-    const uint32_t xl = (uint32_t)x, xh = (uint32_t)((unsigned long long)x >> 32);
-    const uint32_t old = atomicAdd(lo + idx, xl);
-    const uint32_t carry = (uint32_t)((old + xl) < xl);
-    atomicAdd(hi + idx, xh + carry);
-}
-
-// Per-slice preparation (one CTA per slice): the fixed-point scales from the
-// NaN-skipping (min, max) of the slice and max |ww|, and the LUT over Q
-// (first row whose bucket is >= b, packed (first[b], first[b+1])), both shared by
-// every column tile of the slice.  A slice with an infinite value is handed to the
-// exact loop (sorted[s] = 0, *any_unsorted = 1).
-constexpr int FX_PREP_NT = 256;
-struct FxScale { double c, sS, sV, iS, iV, pad0, pad1, pad2; };
-
-__global__ void __launch_bounds__(FX_PREP_NT)
-k_lwa_fx_prep(long s0, int ny, const double* __restrict__ Qref, int increase,
-              int32_t* sorted, int32_t* any_unsorted,
-              const double* __restrict__ rng, int rngC, const double* __restrict__ wmax_part, int n_wmax,
-              FxScale* __restrict__ fxs, uint32_t* __restrict__ lutg)
-{
-    const long s = s0 + blockIdx.x;
-    if (!sorted[s]) return;
-    __shared__ uint16_t first[FX_LUT + 2];
-    __shared__ double swm[FX_PREP_NT / 32];
-    const int tid = threadIdx.x;
-    const double sg = increase ? 1.0 : -1.0;
-    const double* Qg = Qref + s * (long)ny;
-    double wm = 0.0;
-    for (int k = tid; k < n_wmax; k += FX_PREP_NT) wm = fmax(wm, wmax_part[k]);
-    wm = warp_max(wm);
-    if ((tid & 31) == 0) swm[tid >> 5] = wm;
-    const double qmin = sg * Qg[0], qmax = sg * Qg[ny - 1];
-    const float qminf = (float)qmin;
-    const float scalef = (qmax > qmin) ? (float)((double)FX_LUT / (qmax - qmin)) : 0.0f;
-    for (int j = tid; j <= ny; j += FX_PREP_NT) {
-        const int bj = (j < ny) ? fx_bucket((float)(sg * Qg[j]), qminf, scalef) : FX_LUT;
-        const int bp = (j > 0) ? fx_bucket((float)(sg * Qg[j - 1]), qminf, scalef) : -1;
-        for (int b = bp + 1; b <= bj; ++b) first[b] = (uint16_t)j;
-    }
-    __syncthreads();
-    uint32_t* lut = lutg + (size_t)blockIdx.x * FX_LUT;
-    for (int b = tid; b < FX_LUT; b += FX_PREP_NT) lut[b] = (uint32_t)first[b] | ((uint32_t)first[b + 1] << 16);
-    if (tid == 0) {
-        for (int k = 1; k < FX_PREP_NT / 32; ++k) wm = fmax(wm, swm[k]);
-        double lo = CUDART_INF, hi = -CUDART_INF;
-        for (int k = 0; k < rngC; ++k) {
-            lo = fmin(lo, rng[(s * rngC + k) * 2]); hi = fmax(hi, rng[(s * rngC + k) * 2 + 1]);
-        }
-        const double a = sg * lo, b = sg * hi;
-        const double vlo = fmin(a, b), vhi = fmax(a, b);
-        FxScale f;
-        f.c = 0.5 * vlo + 0.5 * vhi;
-        const double vabs = fmax(vhi - f.c, f.c - vlo);
-        const double MV = wm * vabs * 1.0000001, MS = wm;
-        const bool empty = !(lo <= hi);                              // slice without a finite value
-        if (!empty && !(isfinite(MV) && isfinite(MS) && isfinite(f.c))) {  // inf in q or ww: exact loop instead
-            sorted[s] = 0; if (any_unsorted) *any_unsorted = 1;
-        }
-        int hb = 1; while ((1 << hb) < ny + 1) ++hb;                 // sums of up to ny terms
-        const int kb = min(51, 62 - hb) - 1;                         // |X| < 2^(kb+1): fx_rn range and 63-bit column sums
-        const int kS = (MS > 0.0 && isfinite(MS) && !empty) ? kb - ilogb(MS) : 0;
-        const int kV = (MV > 0.0 && isfinite(MV) && !empty) ? kb - ilogb(MV) : 0;
-        if (empty || !isfinite(f.c)) f.c = 0.0;
-        f.sS = scalbn(1.0, kS); f.iS = scalbn(1.0, -kS);
-        f.sV = scalbn(1.0, kV); f.iV = scalbn(1.0, -kV);
-        f.pad0 = f.pad1 = f.pad2 = 0.0;
-        fxs[blockIdx.x] = f;
-    }
-}
-
-// the deposit of one cell; used by the scatter phase (with negated scales: rn() is
-// odd, so rn(-x) = -rn(x) bit for bit) and re-derived by the prefix phase
-__device__ __forceinline__ void fx_terms(double v, double w, double c, double sS, double sV, long long& XS, long long& XV)
-{
-    XS = fx_rn(__dmul_rn(w, sS));
-    XV = fx_rn(__dmul_rn(__dmul_rn(w, __dsub_rn(v, c)), sV));
-}
-// sign-adjusted value of a cell in fp32 (exact) / fp64 and its fp32 image for the LUT
-__device__ __forceinline__ void fx_value(float qraw, float sgf, double, double& v, float& vf) { vf = sgf * qraw; v = (double)vf; }
-__device__ __forceinline__ void fx_value(double qraw, float, double sg, double& v, float& vf) { v = sg * qraw; vf = (float)v; }
-
-#ifndef XC_FX_U
-#define XC_FX_U 4
-#endif
-#ifndef XC_FX_PROBES
-#define XC_FX_PROBES 2
-#endif
-constexpr int FX_U = XC_FX_U;        // rows whose loads are in flight together
-
-template <typename QT, int FX_TC>
-__global__ void __launch_bounds__(FX_SEG * FX_TC, FX_TC <= 8 ? 2 : 1)
-k_lwa_fx(const QT* __restrict__ q, long s0, long sbase, int ny, int nx,
-         const double* __restrict__ Qref, const double* __restrict__ ww,
-         int increase, int part, const int32_t* __restrict__ sorted,
-         const FxScale* __restrict__ fxs, const uint32_t* __restrict__ lutg,
-         double* __restrict__ out)
-{
-    const long s = s0 + blockIdx.y;
-    if (!sorted[s]) return;
-    extern __shared__ __align__(16) unsigned char smem[];
-    constexpr int FX_NT = FX_SEG * FX_TC;
-    static_assert(FX_NT / 32 >= 2 * FX_TC && FX_LUT % FX_NT == 0, "one scan warp per (accumulator, column)");
-    const LwaFxSmem L = lwa_fx_layout(ny, FX_TC);
-    double*    Qs  = reinterpret_cast<double*>(smem + L.off_Q);
-    uint32_t*  far = reinterpret_cast<uint32_t*>(smem + L.off_far);
-    uint32_t*  lut = reinterpret_cast<uint32_t*>(smem + L.off_lut);
-    long long* tot = reinterpret_cast<long long*>(smem + L.off_tot);     // [2][FX_TC][FX_TOTP]
-    const int plane = L.plane;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const double sg = increase ? 1.0 : -1.0;
-    const float sgf = increase ? 1.0f : -1.0f;
-    const double* Qg = Qref + s * (long)ny;
-    const uint32_t* lg = lutg + (size_t)(s - sbase) * FX_LUT;
-    for (int j = tid; j < ny; j += FX_NT) Qs[j] = sg * Qg[j];
-#pragma unroll
-    for (int k = 0; k < FX_LUT / FX_NT; ++k) lut[tid + k * FX_NT] = __ldg(lg + tid + k * FX_NT);
-    {
-        uint4* z = reinterpret_cast<uint4*>(far);
-        for (int k = tid; k < plane; k += FX_NT) z[k] = make_uint4(0u, 0u, 0u, 0u);   // 4 planes of `plane` words
-    }
-    const FxScale* fp = fxs + (s - sbase);
-    const double fc = __ldg(&fp->c), fsS = __ldg(&fp->sS), fsV = __ldg(&fp->sV);
-    __syncthreads();
-    const double qmin = Qs[0], qmax = Qs[ny - 1];
-    const float qminf = (float)qmin;
-    const float scalef = (qmax > qmin) ? (float)((double)FX_LUT / (qmax - qmin)) : 0.0f;
-
-    const bool keep_pos = (part == XC_PART_UPPER) == (increase != 0);
-    const bool use_t1 = (part == XC_PART_ALL) || !keep_pos;   // mask -1 region
-    const bool use_t2 = (part == XC_PART_ALL) || keep_pos;    // mask +1 region
-
-    // thread = (column c, row segment seg); the segments split the rows evenly
-    const int c = tid & (FX_TC - 1), seg = tid / FX_TC;
-    const int i = blockIdx.x * FX_TC + c;
-    const bool col_ok = i < nx;
-    const int r0 = (int)(((long)seg * ny) / FX_SEG), r1 = (int)(((long)(seg + 1) * ny) / FX_SEG);
-    const QT* qc = q + (s * (long)ny + r0) * nx + i;
-    const double* wc = ww + (long)r0 * nx + i;
-    uint32_t* fcol = far + c;                                  // word (slot t, plane k) = fcol[t * FX_TC + k * plane]
-
-    // ---- scatter: one deposit of -X at the far end of each cell's range ----
-    long long ownS = 0, ownV = 0;
-    if (col_ok) {
-        const double nsS = -fsS, nsV = -fsV;
-        const QT* qp = qc; const double* wp = wc;
-        for (int jb = r0; jb < r1; jb += FX_U) {
-            QT qv[FX_U]; double wv[FX_U];
-#pragma unroll
-            for (int u = 0; u < FX_U; ++u) {
-                const bool ok = jb + u < r1;
-                qv[u] = ok ? __ldg(qp + (long)u * nx) : (QT)CUDART_NAN;
-                wv[u] = ok ? __ldg(wp + (long)u * nx) : 0.0;
-            }
-            qp += (long)FX_U * nx; wp += (long)FX_U * nx;
-#pragma unroll
-            for (int u = 0; u < FX_U; ++u) {
-                const int jp = jb + u;
-                double v; float vf;
-                fx_value(qv[u], sgf, sg, v, vf);
-                const double w = wv[u];
-                if (v != v || w != w) continue;                  // NaN cell / NaN weight / past the segment
-                long long NS, NV;                                // -X_S, -X_V
-                fx_terms(v, w, fc, nsS, nsV, NS, NV);
-                const uint32_t pk = lut[fx_bucket(vf, qminf, scalef)];
-                int x = (int)(pk & 0xffffu), e = (int)(pk >> 16);
-                const int e0 = e;                                // rows >= e0 have Q > v
-                while (x < e) { const int mid = (x + e) >> 1; if (Qs[mid] < v) x = mid + 1; else e = mid; }
-                int target = jp + 1;                             // inactive: cancels the own deposit
-                if (x > jp + 1) { if (use_t1) target = x; }      // x = #{Q < v}
-                else {
-                    int h = x;                                   // #{Q <= v}; ties live in v's bucket only
-                    if (h < e0 && Qs[h] == v) {
-                        int y = e0; ++h;
-                        while (h < y) { const int mid = (h + y) >> 1; if (Qs[mid] <= v) h = mid + 1; else y = mid; }
-                    }
-                    if (h <= jp && use_t2) target = h;
-                }
-                ownS -= NS; ownV -= NV;
-                uint32_t* slot = fcol + target * FX_TC;
-                fx_add64(slot, slot + plane, 0, NS);
-                fx_add64(slot + 2 * plane, slot + 3 * plane, 0, NV);
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- prefix down the columns: segment totals, block scan, final walk ----
-    {
-        unsigned long long aSl = 0, aVl = 0; long long aSh = 0, aVh = 0;
-        const uint32_t* sl = fcol + r0 * FX_TC;
-        for (int j = r0; j < r1; ++j, sl += FX_TC) {
-            aSl += sl[0]; aSh += (int32_t)sl[plane]; aVl += sl[2 * plane]; aVh += (int32_t)sl[3 * plane];
-        }
-        tot[c * FX_TOTP + seg] = (long long)aSl + (aSh << 32) + ownS;
-        tot[(FX_TC + c) * FX_TOTP + seg] = (long long)aVl + (aVh << 32) + ownV;
-    }
-    __syncthreads();
-    if (warp < 2 * FX_TC) {                                      // warp = (which, column): exclusive scan over segments
-        long long* row = tot + (size_t)warp * FX_TOTP;
-        const long long a0 = row[2 * lane], a1 = row[2 * lane + 1];
-        long long x = a0 + a1;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(XC_FULL, x, o); if (lane >= o) x += t; }
-        const long long ex = x - (a0 + a1);
-        row[2 * lane] = ex; row[2 * lane + 1] = ex + a0;
-    }
-    __syncthreads();
-    if (col_ok) {
-        const double fiS = __ldg(&fp->iS), fiV = __ldg(&fp->iV);
-        long long RS = tot[c * FX_TOTP + seg], RV = tot[(FX_TC + c) * FX_TOTP + seg];
-        double* op = out + (s * (long)ny + r0) * nx + i;
-        const QT* qp = qc; const double* wp = wc;
-        const uint32_t* sl = fcol + r0 * FX_TC;
-        const double* Qj = Qs + r0;
-        for (int jb = r0; jb < r1; jb += FX_U) {
-            QT qv[FX_U]; double wv[FX_U];
-#pragma unroll
-            for (int u = 0; u < FX_U; ++u) {
-                const bool ok = jb + u < r1;
-                qv[u] = ok ? __ldg(qp + (long)u * nx) : (QT)CUDART_NAN;
-                wv[u] = ok ? __ldg(wp + (long)u * nx) : 0.0;
-            }
-            qp += (long)FX_U * nx; wp += (long)FX_U * nx;
-#pragma unroll
-            for (int u = 0; u < FX_U; ++u) {
-                if (jb + u >= r1) break;
-                RS += (long long)(((unsigned long long)sl[plane] << 32) | sl[0]);
-                RV += (long long)(((unsigned long long)sl[3 * plane] << 32) | sl[2 * plane]);
-                const double Sj = __dmul_rn(fx_to_double(RS), fiS), Vj = __dmul_rn(fx_to_double(RV), fiV);
-                *op = sg * (Vj - (*Qj - fc) * Sj);
-                op += nx; sl += FX_TC; ++Qj;
-                double v; float vf;
-                fx_value(qv[u], sgf, sg, v, vf);
-                if (v == v && wv[u] == wv[u]) {
-                    long long XS, XV;
-                    fx_terms(v, wv[u], fc, fsS, fsV, XS, XV);
-                    RS += XS; RV += XV;
-                }
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------
-// Second-generation fixed-point kernel ("column tiles with register-resident own
-// deposits") for weights that are constant along a row, ww[j][i] = ww_row[j] -- every
-// regular lat-lon, Cartesian and X-Z grid.  Same arithmetic as k_lwa_fx (same scales,
-// same rounding of every term; 2^-kS is folded into the (Q_j - c) table, which is exact --
-// the two kernels agree bit for bit); what changes is where the
-// work is done (ncu of k_lwa_fx: 201 warp-instructions per 32 cells, 64 % of the time on
-// the prefix side):
-//   * no weight loads: -w 2^kV and -rn(w 2^kS) of the ny rows sit in shared memory;
-//   * a thread keeps the own-slot deposit of each of its <= 12 cells in registers
-//     between the scatter and the prefix phase (it owns the same (column, rows) in both),
-//     so the prefix walk neither re-derives it from global memory nor pays four more
-//     atomics: scatter = one 64-bit deposit per accumulator at the FAR end of the range;
-//   * lo and hi word of an accumulator are adjacent: one LDS.64 per accumulator and row
-//     in the two prefix passes, immediate offsets in the unrolled walk;
-//   * the search runs on fp32 thresholds (smallest fp32 > Q_j and >= Q_j: for an fp32
-//     value v, #{Q < v} = #{T_> <= v}), a 2048-bucket LUT bounds it to ~0.3 probes;
-//   * persistent CTAs walk consecutive tiles of the slice-major tile list, so the tables
-//     of a slice are built once per CTA and slice, not once per tile.
-// grid = SM count, block = 1024 = 16 columns x 64 row segments, one CTA per SM.
-constexpr int LC_TC = 16, LC_U = 12, LC_NT = FX_SEG * LC_TC;
-struct LwaColsSmem { size_t farS, farV, nxs, wrow, qc, ta, tb, uni, lut, tot, total; };
-static __host__ __device__ inline LwaColsSmem lwa_cols_layout(int ny, int tbytes)
-{
-    LwaColsSmem L; size_t o = 0;
-    const size_t plane = (size_t)(ny + 1) * LC_TC * 8;
-    const size_t col8 = (size_t)((ny + 1) & ~1) * 8;
-    L.farS = o; o += plane;
-    L.farV = o; o += plane;
-    // per-slice tables, built when a CTA meets a new slice
-    L.nxs = o;  o += col8;                                     // -rn(w 2^kS)
-    L.wrow = o; o += col8;                                     // -w 2^kV
-    L.qc = o;   o += col8;                                     // (Q_j - c) 2^-kS
-    L.ta = o;   o += (size_t)((ny + 2 + 3) & ~3) * tbytes;     // smallest value > Q_j, two +inf entries past the end
-    L.tb = o;   o += (size_t)((ny + 2 + 3) & ~3) * tbytes;     // smallest value >= Q_j
-    // per tile: the LUT (scatter phase) and the segment totals (prefix phase) share one region
-    L.uni = o; L.lut = o; L.tot = o;
-    const size_t a = (size_t)((FX_LUT + 2 + 7) & ~7) * 2, b = (size_t)2 * LC_TC * FX_TOTP * 8;
-    L.total = o + (a > b ? a : b);
-    return L;
-}
-__device__ __forceinline__ void lc_add64(uint32_t a, long long x)
-{
-    asm volatile("{\n\t.reg .u32 o, d, h;\n\t"
-                 "atom.shared.add.u32 o, [%0], %1;\n\t"
-                 "add.cc.u32 d, o, %1;\n\t"
-                 "addc.u32 h, %2, 0;\n\t"
-                 "red.shared.add.u32 [%0+4], h;\n\t}"
-                 :: "r"(a), "r"((uint32_t)x), "r"((uint32_t)((unsigned long long)x >> 32)) : "memory");
-}
-__device__ __forceinline__ long long lc_lds64(uint32_t a)
-{
-    long long v; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(a)); return v;
-}
-// smallest value of the threshold type that is > x (strict) or >= x
-__device__ __forceinline__ float lc_thr(double x, bool strict, float)
-{
-    float f = __double2float_rn(x);
-    const bool fine = strict ? (double)f > x : (double)f >= x;
-    if (!fine) {                                                   // next float above f
-        const int b = __float_as_int(f);
-        f = (f == 0.0f) ? __int_as_float(1) : __int_as_float(f > 0.0f ? b + 1 : b - 1);
-    }
-    return f;
-}
-__device__ __forceinline__ double lc_thr(double x, bool strict, double) { return strict ? nextafter(x, CUDART_INF) : x; }
-
-__device__ __forceinline__ uint32_t lc_keep(uint32_t x) { uint32_t r; asm volatile("mov.b32 %0, %1;" : "=r"(r) : "r"(x)); return r; }
-
-// The scatter phase is written without data-dependent branches: a warp executes every path of a divergent
-// branch, and in the first version of this kernel (divergent search loops, region-1 / region-2 / inactive
-// paths, `continue`s) that made the executed warp-instruction count 2.6x the per-thread count (ncu: 199
-// warp-instructions per 32 cells, same as k_lwa_fx).  Here every cell does the same thing: two independent
-// probes after the LUT (a warp-uniform vote sends the rare denser buckets and exact ties to a loop), the target
-// slot by selects, and ALWAYS one far deposit per accumulator -- a cell without a range deposits at its own
-// slot jp + 1, where the walk's unconditional own deposit cancels it exactly (integers).
-template <typename QT, bool INC>
-__global__ void __launch_bounds__(LC_NT, 1)
-k_lwa_cols(const QT* __restrict__ q, long s0, int nslices, int ny, int nx,
-           const double* __restrict__ Qref, const double* __restrict__ ww_row,
-           int part, const int32_t* __restrict__ sorted,
-           const FxScale* __restrict__ fxs, const uint32_t* __restrict__ lutg,
-           double* __restrict__ out)
-{
-    using TT = QT;                                               // thresholds live in the tracer's own type
-    extern __shared__ __align__(16) unsigned char smem[];
-    const LwaColsSmem L = lwa_cols_layout(ny, (int)sizeof(TT));
-    long long* nxs = reinterpret_cast<long long*>(smem + L.nxs);
-    uint16_t*  lut = reinterpret_cast<uint16_t*>(smem + L.lut);
-    double*    wrow = reinterpret_cast<double*>(smem + L.wrow);
-    TT*        ta = reinterpret_cast<TT*>(smem + L.ta);
-    TT*        tb = reinterpret_cast<TT*>(smem + L.tb);
-    long long* tot = reinterpret_cast<long long*>(smem + L.tot);
-    double*    qcs = reinterpret_cast<double*>(smem + L.qc);
-    const uint32_t sm0 = (uint32_t)__cvta_generic_to_shared(smem);
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr double sg = INC ? 1.0 : -1.0;
-    const bool keep_pos = (part == XC_PART_UPPER) == INC;
-    const bool use_t1 = (part == XC_PART_ALL) || !keep_pos;   // mask -1 region
-    const bool use_t2 = (part == XC_PART_ALL) || keep_pos;    // mask +1 region
-    const int c = tid & (LC_TC - 1), seg = tid / LC_TC;
-    const int r0 = (int)(((long)seg * ny) / FX_SEG), r1 = (int)(((long)(seg + 1) * ny) / FX_SEG);
-    const int tps = (nx + LC_TC - 1) / LC_TC;                  // tiles per slice
-    const long ntiles = (long)nslices * tps;
-    const long t_beg = ntiles * blockIdx.x / gridDim.x, t_end = ntiles * (blockIdx.x + 1) / gridDim.x;
-    // shared-window addresses the compiler must not rebuild from special registers at every use
-    const uint32_t farS_c = lc_keep(sm0 + (uint32_t)L.farS + (uint32_t)c * 8u);
-    const uint32_t farV_c = lc_keep(sm0 + (uint32_t)L.farV + (uint32_t)c * 8u);
-    const uint32_t colS = lc_keep(farS_c + (uint32_t)r0 * (LC_TC * 8)), colV = lc_keep(farV_c + (uint32_t)r0 * (LC_TC * 8));
-    const uint32_t nxs_r0 = lc_keep(sm0 + (uint32_t)L.nxs + (uint32_t)r0 * 8u);
-    const uint32_t wrow_r0 = lc_keep(sm0 + (uint32_t)L.wrow + (uint32_t)r0 * 8u);
-    const uint32_t qcs_r0 = lc_keep(sm0 + (uint32_t)L.qc + (uint32_t)r0 * 8u);
-
-    long cur_slice = -1;
-    double fc = 0.0, fiV = 0.0; float scalef = 0.f, qminf = 0.f;
-    bool slice_ok = false;
-    for (long tile = t_beg; tile < t_end; ++tile) {
-        const long sl = tile / tps; const int tx = (int)(tile - sl * tps);
-        const long s = s0 + sl;
-        const bool fresh = sl != cur_slice;
-        if (fresh) { cur_slice = sl; slice_ok = sorted[s] != 0; }
-        if (!slice_ok) continue;                                  // uniform: the exact loop takes this slice
-        const FxScale* fp = fxs + sl;
-        const double* Qg = Qref + s * (long)ny;
-        // ---- phase 0: zero the planes, (re)build the tables ----
-        __syncthreads();                                          // previous tile's walk is done with the planes / union
-        {
-            uint4* z = reinterpret_cast<uint4*>(smem + L.farS);
-            const int n16 = (ny + 1) * LC_TC;
-            for (int k = tid; k < n16; k += LC_NT) z[k] = make_uint4(0u, 0u, 0u, 0u);
-        }
-        if (fresh) {                                              // tables of this slice (shared by all its tiles)
-            fc = __ldg(&fp->c);
-            const double fsS = __ldg(&fp->sS), fsV = __ldg(&fp->sV), fiS = __ldg(&fp->iS);
-            fiV = __ldg(&fp->iV);
-            for (int j = tid; j < ny + 2; j += LC_NT) {
-                if (j >= ny) { ta[j] = (TT)CUDART_INF; tb[j] = (TT)CUDART_INF; continue; }    // probes may look one past the end
-                const double Qj = sg * Qg[j], w = __ldg(ww_row + j);
-                ta[j] = lc_thr(Qj, true, TT()); tb[j] = lc_thr(Qj, false, TT());
-                wrow[j] = (w == w) ? __dmul_rn(w, -fsV) : 0.0;              // a NaN weight deposits nothing
-                nxs[j] = (w == w) ? fx_rn(__dmul_rn(w, -fsS)) : 0ll;
-                qcs[j] = __dmul_rn(__dsub_rn(Qj, fc), fiS);
-            }
-            const double qmin = sg * Qg[0], qmax = sg * Qg[ny - 1];
-            qminf = (float)qmin;
-            scalef = (qmax > qmin) ? (float)((double)FX_LUT / (qmax - qmin)) : 0.0f;
-        }
-        // LUT: first row of every bucket (+ the end marker), unpacked from the (first[b], first[b+1]) pairs
-        for (int k = tid; k < FX_LUT; k += LC_NT) {
-            const uint32_t pk = __ldg(lutg + (size_t)sl * FX_LUT + k);
-            lut[k] = (uint16_t)(pk & 0xffffu);
-            if (k == FX_LUT - 1) lut[FX_LUT] = (uint16_t)(pk >> 16);
-        }
-        __syncthreads();
-        const TT t_first = ta[0], t_last = ta[ny - 1];            // below / not below every Q: no search
-
-        // ---- phase 1: scatter -- one deposit of -X per accumulator at the far end of each cell's range ----
-        const int i = tx * LC_TC + c;
-        const bool col_ok = i < nx;
-        long long NVr[LC_U];                                      // -X_V of the thread's cells
-        long long ownS = 0;
-        {
-            const QT* qp = q + (s * (long)ny + r0) * nx + (col_ok ? i : 0);
-#pragma unroll
-            for (int u0 = 0; u0 < LC_U; u0 += LC_U / 2) {          // two batches of loads: fewer live registers
-                QT qv[LC_U / 2];
-#pragma unroll
-                for (int k = 0; k < LC_U / 2; ++k) {
-                    qv[k] = (col_ok && r0 + u0 + k < r1) ? __ldg(qp) : (QT)CUDART_NAN;
-                    qp += nx;
-                }
-#pragma unroll
-                for (int k = 0; k < LC_U / 2; ++k) {
-                    // every lane runs the whole body (the vote below is warp-wide); lanes without a cell -- past the
-                    // last column, or the 12th row of an 11-row segment -- carry NaN and skip only the deposits
-                    const int u = u0 + k, jp = r0 + u;
-                    const bool live = col_ok && jp < r1;
-                    const TT vt = INC ? (TT)qv[k] : -(TT)qv[k];
-                    const double v = (double)vt;
-                    const float vf = (float)vt;
-                    double wn; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(wn) : "r"(wrow_r0 + (live ? u * 8 : 0)));
-                    const long long NV = live ? fx_rn(__dmul_rn(__dsub_rn(v, fc), wn)) : 0ll;      // NaN -> 0
-                    const int bk = fx_bucket(vf, qminf, scalef);
-                    int x0 = (int)lut[bk], cnt = (int)lut[bk + 1] - x0;
-                    if (vt >= t_last) { x0 = ny; cnt = 0; }                  // above every Q (the end buckets are the dense ones)
-                    if (vt < t_first) { x0 = 0; cnt = 0; }
-                    const TT t0 = ta[x0], t1 = ta[x0 + 1];
-                    int x = x0 + ((cnt > 0 && t0 <= vt) ? 1 : 0) + ((cnt > 1 && t1 <= vt) ? 1 : 0);    // #{Q < v}
-                    int h = x;                                                                           // #{Q <= v}
-                    const bool odd = live && (cnt > 2 || tb[x] <= vt);       // denser bucket, or an exact tie
-                    if (__any_sync(XC_FULL, odd)) {
-                        if (odd) {
-                            x = x0; int e = x0 + cnt;
-                            while (x < e) { const int mid = (x + e) >> 1; if (ta[mid] <= vt) x = mid + 1; else e = mid; }
-                            h = x;
-                            while (h < ny && tb[h] <= vt) ++h;
-                        }
-                    }
-                    int target = (x > jp + 1 && use_t1) ? x : ((h <= jp && use_t2) ? h : jp + 1);
-                    if (!(vt == vt)) target = jp + 1;                        // NaN cell: cancels at its own slot
-                    NVr[u] = NV;
-                    if (live) {
-                        const long long NS = lc_lds64(nxs_r0 + u * 8);
-                        const uint32_t off = (uint32_t)target * (LC_TC * 8);
-                        lc_add64(farS_c + off, NS);
-                        lc_add64(farV_c + off, NV);
-                        ownS -= NS;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-
-        // ---- phase 2: segment totals, block scan over the 64 segments of every (accumulator, column) ----
-        {
-            long long aS = ownS, aV = 0;
-#pragma unroll
-            for (int u = 0; u < LC_U; ++u) {
-                aV -= NVr[u];                                             // own deposits: +X at slot jp + 1
-                if (r0 + u < r1) { aS += lc_lds64(colS + u * (LC_TC * 8)); aV += lc_lds64(colV + u * (LC_TC * 8)); }
-            }
-            // the shared region changes hands here: LUT -> totals; every thread is past the scatter phase
-            tot[c * FX_TOTP + seg] = aS;
-            tot[(LC_TC + c) * FX_TOTP + seg] = aV;
-        }
-        __syncthreads();
-        {                                                         // warp = (accumulator, column): exclusive scan over segments
-            long long* row = tot + (size_t)warp * FX_TOTP;
-            const long long a0 = row[2 * lane], a1 = row[2 * lane + 1];
-            long long x = a0 + a1;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(XC_FULL, x, o); if (lane >= o) x += t; }
-            const long long ex = x - (a0 + a1);
-            row[2 * lane] = ex; row[2 * lane + 1] = ex + a0;
-        }
-        __syncthreads();
-
-        // ---- phase 3: the walk ----
-        if (col_ok) {
-            long long RS = tot[c * FX_TOTP + seg], RV = tot[(LC_TC + c) * FX_TOTP + seg];
-            double* op = out + (s * (long)ny + r0) * nx + i;
-#pragma unroll
-            for (int u = 0; u < LC_U; ++u) {
-                if (r0 + u >= r1) break;
-                RS += lc_lds64(colS + u * (LC_TC * 8));
-                RV += lc_lds64(colV + u * (LC_TC * 8));
-                double qc; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(qc) : "r"(qcs_r0 + u * 8));
-                const double Vj = __dmul_rn(fx_to_double(RV), fiV);
-                *op = sg * (Vj - qc * fx_to_double(RS));
-                op += nx;
-                RS -= lc_lds64(nxs_r0 + u * 8);                           // own deposits of cell r0 + u, at slot r0 + u + 1
-                RV -= NVr[u];
-            }
-        }
-    }
-}
-
 // NaN-skipping (min, max) of every slice in rngC partials (stand-alone xc_lwa; the
 // fused batch already has them from the levels stage) and max |ww|
 template <typename QT>
@@ -1011,7 +440,7 @@ __global__ void __launch_bounds__(256)
 k_lwa_brute(const QT* __restrict__ q, long S, int ny, int nx,
             const double* __restrict__ Qref, const double* __restrict__ ww,
             int increase, int part, int variant, const int32_t* __restrict__ skip,
-            const int32_t* __restrict__ gate, double* __restrict__ out)
+            const int32_t* __restrict__ gate, double* __restrict__ out, int out_f32)
 {
     if (gate && *gate == 0) return;            // every slice went down the fast path
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -1044,7 +473,8 @@ k_lwa_brute(const QT* __restrict__ q, long S, int ny, int nx,
                     if (!isnan(term)) acc += term;
                 }
             }
-            out[(s * ny + j) * (long)nx + i] = -acc;
+            if (out_f32) reinterpret_cast<float*>(out)[(s * ny + j) * (long)nx + i] = (float)-acc;
+            else out[(s * ny + j) * (long)nx + i] = -acc;
         }
     }
 }
@@ -1177,8 +607,6 @@ extern "C" int xc_lwa_weights(const void* dA, int dA_dtype, long P, double* ww,
 
 constexpr int LWA_RNG_C = 8;        // partial (min, max) CTAs per slice in the stand-alone path
 constexpr int LWA_WMAX_N = 128;     // partial max |ww| CTAs
-template <typename QT, typename... A> static const QT* lwa_qptr(void (*)(const QT*, A...)) { return nullptr; }
-constexpr long FX_CHUNK = 1024;     // slices per fixed-point launch (bounds the per-slice LUT scratch)
 size_t xc::lwa_scratch_doubles(long S, bool have_minmax)
 {
     const long Sp = S > 0 ? S : 0, ch = Sp < FX_CHUNK ? Sp : FX_CHUNK;
@@ -1232,7 +660,7 @@ int xc::lwa_wmax(const double* ww, long P, double* parts, void* stream)
 int xc::lwa_impl(const void* q, int q_dtype, long S, int n_eq, int n_x, const double* Qref, const double* ww,
                  int increase, int part, int variant, double* out, int32_t* sorted,
                  int32_t* any_unsorted, bool flags_ready, const double* minmax, double* scratch, void* stream,
-                 const double* wmax_ready, const double* ww_row)
+                 const double* wmax_ready, const double* ww_row, int out_f32)
 {
     XC_REQUIRE(q && Qref && ww && out, "xc_lwa: null pointer");
     XC_REQUIRE(S > 0 && n_eq >= 1 && n_x >= 1, "xc_lwa: need S>0, n_eq>=1, n_x>=1");
@@ -1244,9 +672,10 @@ int xc::lwa_impl(const void* q, int q_dtype, long S, int n_eq, int n_x, const do
     const bool match = lwa_use_match();
     const int qbytes = q_dtype == XC_F32 ? 4 : 8;
     const int tc = (n_eq < 65535) ? lwa_pick_tc(n_eq, qbytes, !match) : 0;
-    const int fx_tc = lwa_fx_layout(n_eq, 16).total <= 227 * 1024 ? 16 : 8;
-    const LwaFxSmem FL = lwa_fx_layout(n_eq, fx_tc);
-    const bool fx = (variant == 1) && lwa_use_fx() && scratch && n_eq < 65535 && FL.total <= 227 * 1024;
+    static const char* no_cols0 = getenv("XCB200_NO_LWA_COLS");
+    const bool fx = (variant == 1) && lwa_use_fx() && scratch && n_eq < 65535 &&
+                    (lwa_fx_fits(n_eq) || (ww_row && !no_cols0 && lwa_cols_fits(n_eq, qbytes)));
+    XC_REQUIRE(!out_f32 || fx, "xc_keff_lwa_batch: lwa_f32 needs the fixed-point column-tile kernel");
     const bool fast = fx || ((variant == 1) && tc >= 1 && (size_t)tc * (n_eq + 2) * 16 >= (size_t)(LWA_LUT + 1) * 2);
     if (fast && !flags_ready) {
         k_check_sorted<<<(unsigned)S, 256, 0, st>>>(Qref, n_eq, increase, sorted);
@@ -1277,39 +706,16 @@ int xc::lwa_impl(const void* q, int q_dtype, long S, int n_eq, int n_x, const do
         FxScale* fxs = reinterpret_cast<FxScale*>(cur);
         const long ch = S < FX_CHUNK ? S : FX_CHUNK;
         uint32_t* lutg = reinterpret_cast<uint32_t*>(cur + (size_t)ch * sizeof(FxScale));
-        auto launch = [&](auto kern, int tcv, long s0, long ns) -> int {
-            XC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL.total));
-            dim3 grid((unsigned)((n_x + tcv - 1) / tcv), (unsigned)ns);
-            kern<<<grid, FX_SEG * tcv, FL.total, st>>>((decltype(lwa_qptr(kern)))q, s0, s0, n_eq, n_x, Qref, ww, increase, part, sorted, fxs, lutg, out);
-            XC_LAUNCH_OK();
-            return 0;
-        };
+        // row-constant weights: the column-tile kernel with register-resident own deposits (lwa_cols.cu);
+        // general weights: k_lwa_fx (lwa_fx.cu)
+        static const char* no_cols = getenv("XCB200_NO_LWA_COLS");
+        const bool cols = ww_row && !no_cols && lwa_cols_fits(n_eq, qbytes);
+        XC_REQUIRE(cols || !out_f32, "xc_keff_lwa_batch: lwa_f32 needs the column-tile kernel (row-constant weights, n_y <= 768)");
         for (long s0 = 0; s0 < S; s0 += FX_CHUNK) {
             const long ns = S - s0 < FX_CHUNK ? S - s0 : FX_CHUNK;
-            k_lwa_fx_prep<<<(unsigned)ns, FX_PREP_NT, 0, st>>>(s0, n_eq, Qref, increase, sorted, any_unsorted,
-                                                               rng, rngC, wparts, LWA_WMAX_N, fxs, lutg);
-            XC_LAUNCH_OK();
-            int rc;
-            // row-constant weights: the column-tile kernel with register-resident own deposits
-            static const char* no_cols = getenv("XCB200_NO_LWA_COLS");
-            const size_t cols_smem = lwa_cols_layout(n_eq, qbytes).total;
-            if (ww_row && !no_cols && n_eq <= FX_SEG * LC_U && n_eq >= 2 && cols_smem <= 227 * 1024) {
-                const long tiles = ns * ((n_x + LC_TC - 1) / LC_TC);
-                const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
-                auto go = [&](auto kern, auto qptr) -> int {
-                    XC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_smem));
-                    kern<<<grid, LC_NT, cols_smem, st>>>(qptr, s0, (int)ns, n_eq, n_x, Qref, ww_row, part, sorted, fxs, lutg, out);
-                    return 0;
-                };
-                int rcc;
-                if (q_dtype == XC_F32) rcc = increase ? go(k_lwa_cols<float, true>, (const float*)q) : go(k_lwa_cols<float, false>, (const float*)q);
-                else                   rcc = increase ? go(k_lwa_cols<double, true>, (const double*)q) : go(k_lwa_cols<double, false>, (const double*)q);
-                if (rcc) return rcc;
-                XC_LAUNCH_OK();
-                continue;
-            }
-            if (q_dtype == XC_F32) rc = fx_tc == 16 ? launch(k_lwa_fx<float, 16>, 16, s0, ns) : launch(k_lwa_fx<float, 8>, 8, s0, ns);
-            else                   rc = fx_tc == 16 ? launch(k_lwa_fx<double, 16>, 16, s0, ns) : launch(k_lwa_fx<double, 8>, 8, s0, ns);
+            if (lwa_fx_prep_launch(s0, ns, n_eq, Qref, increase, sorted, any_unsorted, rng, rngC, wparts, LWA_WMAX_N, fxs, lutg, stream)) return 1;
+            const int rc = cols ? lwa_cols_launch(q, q_dtype, s0, ns, n_eq, n_x, Qref, ww_row, increase, part, sorted, fxs, lutg, out, out_f32, stream)
+                                : lwa_fx_launch(q, q_dtype, s0, ns, n_eq, n_x, Qref, ww, increase, part, sorted, fxs, lutg, out, stream);
             if (rc) return rc;
         }
     } else if (fast) {
@@ -1347,10 +753,10 @@ int xc::lwa_impl(const void* q, int q_dtype, long S, int n_eq, int n_x, const do
     unsigned nb = (unsigned)(sm_count() * (gated ? 1 : 8));
     if (q_dtype == XC_F32)
         k_lwa_brute<float><<<nb, blk, 0, st>>>((const float*)q, S, n_eq, n_x, Qref, ww, increase, part,
-                                               variant, (fast || fast2) ? sorted : nullptr, gated ? any_unsorted : nullptr, out);
+                                               variant, (fast || fast2) ? sorted : nullptr, gated ? any_unsorted : nullptr, out, out_f32);
     else
         k_lwa_brute<double><<<nb, blk, 0, st>>>((const double*)q, S, n_eq, n_x, Qref, ww, increase, part,
-                                                variant, (fast || fast2) ? sorted : nullptr, gated ? any_unsorted : nullptr, out);
+                                                variant, (fast || fast2) ? sorted : nullptr, gated ? any_unsorted : nullptr, out, out_f32);
     XC_LAUNCH_OK();
     return 0;
 }

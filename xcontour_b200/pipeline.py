@@ -98,7 +98,7 @@ class KeffLwaPlan(object):
     def workspace_bytes(self, S):
         return _lib.load().xc_keff_lwa_batch_workspace_bytes(S, self.ny, self.nx, self.N)
 
-    def alloc_outputs(self, S, lwa=True):
+    def alloc_outputs(self, S, lwa=True, lwa_dtype=torch.float64):
         """Output tensors of one batch.  The nine contour-space results are slabs of ONE buffer
         ``out.packed`` [9, S, N] (CONTOUR_VARS order), so that gathering them across ranks is a single
         collective on a single buffer with no packing copies (ContourGather)."""
@@ -108,7 +108,8 @@ class KeffLwaPlan(object):
         out.packed = packed
         out["Qref"] = torch.empty((S, self.ny), dtype=torch.float64, device=dev)
         if lwa:
-            out["lwa"] = torch.empty((S, self.ny, self.nx), dtype=torch.float64, device=dev)
+            # lwa_dtype=torch.float32 is an opt-in that is NOT a drop-in result (the fp64 field rounded once)
+            out["lwa"] = torch.empty((S, self.ny, self.nx), dtype=lwa_dtype, device=dev)
         return out
 
     def run(self, q, grdS=None, out=None, ws=None, stage_ms=None):
@@ -146,6 +147,7 @@ class KeffLwaPlan(object):
             setattr(a, k, out[k].data_ptr() if k in out else None)
         a.Qref = out["Qref"].data_ptr() if "Qref" in out else None
         a.lwa = out["lwa"].data_ptr() if "lwa" in out else None
+        a.lwa_f32 = int("lwa" in out and out["lwa"].dtype == torch.float32)
         a.stage_ms = ctypes.cast(stage_ms, ctypes.c_void_p) if stage_ms is not None else None
         check(lib.xc_keff_lwa_batch(ctypes.byref(a), ctypes.c_void_p(ws.data_ptr()), nb, ops.stream_ptr()))
         return out
@@ -203,12 +205,12 @@ class HostStreamer(object):
     copies of neighbouring batches overlap the kernels of the current one (H2D,
     kernels and D2H of a batch are ordered on that batch's own stream)."""
 
-    def __init__(self, plan, batch, q_dtype=torch.float32, copy_lwa=True, nbuf=3):
+    def __init__(self, plan, batch, q_dtype=torch.float32, copy_lwa=True, nbuf=3, lwa_dtype=torch.float64):
         self.plan, self.batch, self.copy_lwa, self.nbuf = plan, int(batch), copy_lwa, int(nbuf)
         dev = plan.dA.device
         self.streams = [torch.cuda.Stream(device=dev) for _ in range(self.nbuf)]
         self.qdev = [torch.empty((batch, plan.ny, plan.nx), dtype=q_dtype, device=dev) for _ in range(self.nbuf)]
-        self.outs = [plan.alloc_outputs(batch) for _ in range(self.nbuf)]
+        self.outs = [plan.alloc_outputs(batch, lwa_dtype=lwa_dtype) for _ in range(self.nbuf)]
         self.ws = [torch.empty(plan.workspace_bytes(batch), dtype=torch.uint8, device=dev) for _ in range(self.nbuf)]
         self.host = [{k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in o.items()
                       if copy_lwa or k != "lwa"} for o in self.outs]
