@@ -323,13 +323,13 @@ def test_gradient_wrt_area_follows_the_contour_coordinate(ops, vort, ldt):
     import xcontour_b200 as xb
     lat, lon, q = vort
     q = q[::4, ::4].copy(); lat = lat[::4].copy(); lon = lon[::4].copy()
-    dA = O.latlon_cell_area(lat, lon).astype(np.float32)
+    dA = O.latlon_cell_area(lat, lon)                           # fp64: the strict path then sums in fp64 in the reference too
     coords = {"latitude": lat, "longitude": lon}
     tr = xb.DataArray(q, dims=("latitude", "longitude"), coords=coords, name="pv")
     dAx = xb.DataArray(dA, dims=("latitude", "longitude"), coords=coords)
     lo, hi = float(q.min()), float(q.max())
     rng = np.random.default_rng(2)
-    g = np.abs(rng.standard_normal(q.shape)).astype(np.float32)
+    g = np.abs(rng.standard_normal(q.shape))
     gx = xb.DataArray(g, dims=("latitude", "longitude"), coords=coords, name="g")
     for levels in ((lo + (hi - lo) * np.linspace(0.02, 0.98, 23) ** 1.7).astype(ldt),          # non-uniform
                    np.linspace(lo, hi, 23).astype(ldt)[2:-2] if ldt == np.float64 else
@@ -361,37 +361,40 @@ def test_gradient_wrt_area_follows_the_contour_coordinate(ops, vort, ldt):
 def test_contour_gather_nccl_single_rank_roundtrip(ops):
     """ContourGather (packed [9, S, N] all-gather on a side stream, NCCL) on a one-rank group: what lands in the
     receive buffer is bit-for-bit what plan.run produced, for two batches in flight; the world-size-2 logic of the
-    dict-based gather is covered on gloo in tests/test_oracle.py."""
-    import os
-    import torch.distributed as dist
-    from xcontour_b200.pipeline import CONTOUR_VARS, ContourGather, KeffLwaPlan
-    lat, lon, q = synth_c4(6, 91, 180)
-    dA = O.latlon_cell_area(lat, lon).astype(np.float32)
-    plan = KeffLwaPlan(lat, lon, dA, 41)
-    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    os.environ.setdefault("MASTER_PORT", "29577")
-    created = not dist.is_initialized()
-    if created:
-        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", torch.cuda.current_device()))
-    try:
-        g = ContourGather(3, 41, torch.device("cuda", torch.cuda.current_device()), nbuf=2)
-        qd = dev(ops, q)
-        outs = [plan.alloc_outputs(3, lwa=False), plan.alloc_outputs(3, lwa=False)]
-        recvs = []
-        for b in range(2):
-            plan.run(qd[3 * b:3 * b + 3], out=outs[b])
-            recvs.append(g.launch(outs[b].packed)[0])
-        g.wait()
-        torch.cuda.synchronize()
-        for b in range(2):
-            assert recvs[b].shape == (1, len(CONTOUR_VARS), 3, 41)
-            assert torch.equal(recvs[b][0].nan_to_num(), outs[b].packed.nan_to_num())
-            un = ContourGather.unpack(recvs[b])
-            for k in CONTOUR_VARS:
-                assert torch.equal(un[k].nan_to_num(), outs[b][k].nan_to_num())
-    finally:
-        if created:
-            dist.destroy_process_group()
+    dict-based gather is covered on gloo in tests/test_oracle.py.  Runs in its own process under a hard timeout
+    (a collective that cannot initialise must fail this test, not hang the suite)."""
+    import subprocess, sys
+    from conftest import ROOT
+    code = (
+        "import os, sys, numpy as np, torch; sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, 'tests'))\n"
+        "import torch.distributed as dist\n"
+        "from conftest import synth_c4\n"
+        "from xcontour_b200 import ops\n"
+        "from xcontour_b200.utils import latlon_cell_area\n"
+        "from xcontour_b200.pipeline import CONTOUR_VARS, ContourGather, KeffLwaPlan\n"
+        "lat, lon, q = synth_c4(6, 91, 180)\n"
+        "dA = latlon_cell_area(lat, lon).astype(np.float32)\n"
+        "plan = KeffLwaPlan(lat, lon, dA, 41)\n"
+        "os.environ.setdefault('MASTER_ADDR', '127.0.0.1'); os.environ.setdefault('MASTER_PORT', '29577')\n"
+        "dist.init_process_group('nccl', rank=0, world_size=1, device_id=torch.device('cuda', 0))\n"
+        "g = ContourGather(3, 41, torch.device('cuda', 0), nbuf=2)\n"
+        "qd = ops.to_dev(q)\n"
+        "outs = [plan.alloc_outputs(3, lwa=False), plan.alloc_outputs(3, lwa=False)]\n"
+        "recvs = []\n"
+        "for b in range(2):\n"
+        "    plan.run(qd[3 * b:3 * b + 3], out=outs[b])\n"
+        "    recvs.append(g.launch(outs[b].packed)[0])\n"
+        "g.wait(); torch.cuda.synchronize()\n"
+        "for b in range(2):\n"
+        "    assert recvs[b].shape == (1, len(CONTOUR_VARS), 3, 41)\n"
+        "    assert torch.equal(recvs[b][0].nan_to_num(), outs[b].packed.nan_to_num())\n"
+        "    un = ContourGather.unpack(recvs[b])\n"
+        "    for k in CONTOUR_VARS:\n"
+        "        assert torch.equal(un[k].nan_to_num(), outs[b][k].nan_to_num())\n"
+        "dist.destroy_process_group()\n"
+        "print('gather ok')\n" % (ROOT, ROOT))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=180)
+    assert r.returncode == 0 and "gather ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def test_lwa_f32_opt_in_is_the_fp64_field_rounded_once(ops):

@@ -318,3 +318,14 @@ def test_gradient_wrt_area_uses_the_contour_coordinate():
     assert np.allclose(got[1:-1], g(f) / g(a), rtol=1e-12)
     assert np.array_equal(O.cal_gradient_wrt_area(f, a), O.cal_gradient_wrt_area(f, a, var_coord=np.arange(12.0), area_coord=np.arange(12.0)))
     assert not np.allclose(got[1:-1], O.cal_gradient_wrt_area(f, a)[1:-1], rtol=1e-3)
+
+
+def test_workspace_planning_terminates_for_every_benchmark_shape():
+    """Host-side planning (no GPU needed): xc_keff_lwa_batch_workspace_bytes walks the row-march planner with the
+    worst-case flags; at config 5 (N = 2048) no row count fits the two-CTA shared-memory budget for row-dependent
+    areas and the shrink loop once stalled at 4 rows."""
+    from xcontour_b200 import _lib
+    lib = _lib.load()
+    for args in ((1, 4096, 8192, 2048), (4, 4096, 8192, 2048), (32, 721, 1440, 361), (64, 721, 1440, 361),
+                 (3, 83, 152, 47), (1, 8, 8, 2048), (5, 2, 8, 4), (100000, 721, 1440, 361)):
+        assert lib.xc_keff_lwa_batch_workspace_bytes(*args) > 0

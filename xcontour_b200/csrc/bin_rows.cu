@@ -322,6 +322,17 @@ k_bin_rows(const BinRowsParams p)
                         (unsigned)__double2hiint(G[0]) < hi_limit && (unsigned)__double2hiint(G[1]) < hi_limit &&
                         (unsigned)__double2hiint(G[2]) < hi_limit && (unsigned)__double2hiint(G[3]) < hi_limit);
         if (normal && __all_sync(XC_FULL, ok)) {
+            // smooth stretch of the field: every lane's four cells sit in one bin -> one counter bump and one 96-bit
+            // add per lane instead of four (the lanes of such a step share one or two bins, so the atomics would
+            // serialise on them); the four terms are summed in fp64 first, in a fixed order
+            const bool one = !act || (b[0] == b[1] && b[1] == b[2] && b[2] == b[3]);
+            if (__all_sync(XC_FULL, one)) {
+                if (act) {
+                    br_red(crow + (uint32_t)b[0] * 4u, cinc * 4u);
+                    br_add96<PLB>(acc_sh + (uint32_t)b[0] * (COPIES * 4u), __dadd_rn(__dadd_rn(G[0], G[1]), __dadd_rn(G[2], G[3])));
+                }
+                return;
+            }
             if (act) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) br_red(crow + (uint32_t)b[c] * 4u, cinc);
@@ -411,15 +422,16 @@ BinRowsPlan bin_rows_plan(long S, int ny, int nx, int N, int uniform_dA, int any
         return pl.small ? bin_rows_layout<4 * 512>(N, rp, uni, deg).total : bin_rows_layout<2 * 2048>(N, rp, uni, deg).total;
     };
     const size_t budget = 110 * 1024;                                // two CTAs per SM
-    while (lay(rows_per) > budget) {
+    while (lay(rows_per) > budget) {                                 // strictly decreasing: 111, 82, 60, ... 4, 2
         if (rows_per <= 2) return pl;
-        rows_per = (rows_per * 3 / 4 + 1) & ~1;
+        const int next = (rows_per * 3 / 4) & ~1;
+        rows_per = next >= 2 ? next : 2;
     }
     pl.rows_per = rows_per;
     pl.C = (long)((ny + rows_per - 1) / rows_per) * pl.strips;
     pl.smem = lay(rows_per);
     const long cells = (long)rows_per * pl.strip_w;
-    pl.hbits = 12; while ((1L << pl.hbits) < cells) ++pl.hbits;     // >= 12: terms stay below 2^84 (br_add96)
+    pl.hbits = 14; while ((1L << pl.hbits) < cells) ++pl.hbits;     // >= 14: a thread's four summed terms stay below 2^84 (br_add96)
     pl.ok = pl.C <= 65535 && pl.hbits <= 30 && pl.strip_w <= 65535;
     return pl;
 }

@@ -25,7 +25,7 @@ namespace xc {
 //   * persistent CTAs walk consecutive tiles of the slice-major tile list, so the tables
 //     of a slice are built once per CTA and slice, not once per tile.
 // grid = SM count, block = 1024 = 16 columns x 64 row segments, one CTA per SM.
-constexpr int LC_TC = 16, LC_U = 12, LC_NT = FX_SEG * LC_TC;
+constexpr int LC_TC = 16;                  // columns per tile; threads = row segments (64, or 32 with twice the rows each) x LC_TC
 struct LwaColsSmem { size_t farS, farV, nxs, wrow, qc, ta, uni, lut, tot, total; };
 // `ny` here is the compile-time row CAPACITY of the instantiation (256 / 512 / 736), not the run-time row count:
 // every offset is then a constant and a table access is one instruction with an immediate (ncu of the run-time
@@ -45,7 +45,7 @@ static __host__ __device__ constexpr LwaColsSmem lwa_cols_layout(int ny, int tby
     L.ta = o;   o += (size_t)((ny + 2 + 3) & ~3) * tbytes;     // smallest value > Q_j, two +inf entries past the end
     // per tile: the LUT (scatter phase) and the segment totals (prefix phase) share one region
     L.uni = o; L.lut = o; L.tot = o;
-    const size_t a = (size_t)((FX_LUT + 2 + 7) & ~7) * 2, b = (size_t)2 * LC_TC * FX_TOTP * 8;
+    const size_t a = (size_t)((FX_LUT + 2 + 7) & ~7) * 2, b = (size_t)2 * LC_TC * FX_TOTP * 8;      // (totals: sized for 64 segments)
     L.total = o + (a > b ? a : b);
     return L;
 }
@@ -81,8 +81,8 @@ __device__ __forceinline__ double lc_thr(double x, double) { return nextafter(x,
 //   B  the target slot by selects and ALWAYS one far deposit per accumulator -- a cell without a range (or a NaN
 //      cell) deposits at its own slot jp + 1, where the walk's unconditional own deposit cancels it exactly.
 // Exact ties v == Q_j need no care: such a row contributes w (v - Q_j) = 0 whichever side it is counted on.
-template <typename QT, bool INC, int NYCAP>
-__global__ void __launch_bounds__(LC_NT, 1)
+template <typename QT, bool INC, int NYCAP, int SEG>
+__global__ void __launch_bounds__(SEG * LC_TC, 1)
 k_lwa_cols(const QT* __restrict__ q, long s0, int nslices, int ny, int nx,
            const double* __restrict__ Qref, const double* __restrict__ ww_row,
            int part, const int32_t* __restrict__ sorted,
@@ -91,6 +91,8 @@ k_lwa_cols(const QT* __restrict__ q, long s0, int nslices, int ny, int nx,
 {
     using TT = QT;                                               // thresholds live in the tracer's own type
     constexpr int LC_B = 4;                                      // cells per batch (LC_U is a multiple)
+    constexpr int LC_NT = SEG * LC_TC;
+    constexpr int LC_U = ((NYCAP + SEG - 1) / SEG + LC_B - 1) / LC_B * LC_B;      // rows a thread owns, at most
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr LwaColsSmem L = lwa_cols_layout(NYCAP, (int)sizeof(TT));
     long long* nxs = reinterpret_cast<long long*>(smem + L.nxs);
@@ -106,7 +108,7 @@ k_lwa_cols(const QT* __restrict__ q, long s0, int nslices, int ny, int nx,
     const bool use_t1 = (part == XC_PART_ALL) || !keep_pos;   // mask -1 region
     const bool use_t2 = (part == XC_PART_ALL) || keep_pos;    // mask +1 region
     const int c = tid & (LC_TC - 1), seg = tid / LC_TC;
-    const int r0 = (int)(((long)seg * ny) / FX_SEG), r1 = (int)(((long)(seg + 1) * ny) / FX_SEG);
+    const int r0 = (int)(((long)seg * ny) / SEG), r1 = (int)(((long)(seg + 1) * ny) / SEG);
     const int tps = (nx + LC_TC - 1) / LC_TC;                  // tiles per slice
     const long ntiles = (long)nslices * tps;
     const long t_beg = ntiles * blockIdx.x / gridDim.x, t_end = ntiles * (blockIdx.x + 1) / gridDim.x;
@@ -130,9 +132,10 @@ k_lwa_cols(const QT* __restrict__ q, long s0, int nslices, int ny, int nx,
         // ---- phase 0: zero the planes, tables of a new slice, LUT ----
         __syncthreads();                                          // previous tile's walk is done with the planes / totals
         {
-            uint4* z = reinterpret_cast<uint4*>(smem + L.farS);
-            const int n16 = (ny + 1) * LC_TC;
-            for (int k = tid; k < n16; k += LC_NT) z[k] = make_uint4(0u, 0u, 0u, 0u);
+            uint4* zS = reinterpret_cast<uint4*>(smem + L.farS);          // the planes are NYCAP + 1 slots apart: zero the
+            uint4* zV = reinterpret_cast<uint4*>(smem + L.farV);          // ny + 1 slots in use of each
+            const int n16 = (ny + 1) * (LC_TC / 2);
+            for (int k = tid; k < n16; k += LC_NT) { zS[k] = make_uint4(0u, 0u, 0u, 0u); zV[k] = make_uint4(0u, 0u, 0u, 0u); }
         }
         if (fresh) {                                              // tables of this slice (shared by all its tiles)
             fc = __ldg(&fp->c);
@@ -229,14 +232,19 @@ k_lwa_cols(const QT* __restrict__ q, long s0, int nslices, int ny, int nx,
             tot[(LC_TC + c) * FX_TOTP + seg] = aV;
         }
         __syncthreads();
-        {                                                         // warp = (accumulator, column): exclusive scan over segments
-            long long* row = tot + (size_t)warp * FX_TOTP;
-            const long long a0 = row[2 * lane], a1 = row[2 * lane + 1];
-            long long x = a0 + a1;
+        {                                                         // a warp per (accumulator, column) row: exclusive scan over segments
+            constexpr int RPW = (2 * LC_TC) / (LC_NT / 32), EPL = SEG / 32;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(XC_FULL, x, o); if (lane >= o) x += t; }
-            const long long ex = x - (a0 + a1);
-            row[2 * lane] = ex; row[2 * lane + 1] = ex + a0;
+            for (int rr = 0; rr < RPW; ++rr) {
+                long long* row = tot + (size_t)(warp * RPW + rr) * FX_TOTP;
+                const long long a0 = row[EPL * lane], a1 = EPL == 2 ? row[2 * lane + 1] : 0ll;
+                long long x = a0 + a1;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(XC_FULL, x, o); if (lane >= o) x += t; }
+                const long long ex = x - (a0 + a1);
+                row[EPL * lane] = ex;
+                if (EPL == 2) row[2 * lane + 1] = ex + a0;
+            }
         }
         __syncthreads();
 
@@ -272,7 +280,7 @@ static int lwa_cols_cap(int n_eq) { return n_eq <= 256 ? 256 : n_eq <= 512 ? 512
 bool xc::lwa_cols_fits(int n_eq, int qbytes)
 {
     const int cap = lwa_cols_cap(n_eq);
-    return n_eq <= FX_SEG * LC_U && n_eq >= 2 && cap > 0 && lwa_cols_layout(cap, qbytes).total <= 227 * 1024;
+    return n_eq >= 2 && cap > 0 && lwa_cols_layout(cap, qbytes).total <= 227 * 1024;
 }
 
 int xc::lwa_cols_launch(const void* q, int q_dtype, long s0, long ns, int n_eq, int n_x, const double* Qref, const double* ww_row,
@@ -283,13 +291,19 @@ int xc::lwa_cols_launch(const void* q, int q_dtype, long s0, long ns, int n_eq, 
     const size_t smem = lwa_cols_layout(cap, q_dtype == XC_F32 ? 4 : 8).total;
     const long tiles = ns * ((n_x + LC_TC - 1) / LC_TC);
     const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
-    auto go = [&](auto kern, auto qptr) -> int {
+    auto go = [&](auto kern, auto qptr, int nt) -> int {
         XC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, LC_NT, smem, (cudaStream_t)stream>>>(qptr, s0, (int)ns, n_eq, n_x, Qref, ww_row, part, sorted, fxs, lutg, out, out_f32);
+        kern<<<grid, nt, smem, (cudaStream_t)stream>>>(qptr, s0, (int)ns, n_eq, n_x, Qref, ww_row, part, sorted, fxs, lutg, out, out_f32);
         XC_LAUNCH_OK();
         return 0;
     };
-#define XC_LC_GO(QT, CAP) (increase ? go(k_lwa_cols<QT, true, CAP>, (const QT*)q) : go(k_lwa_cols<QT, false, CAP>, (const QT*)q))
+    // XCB200_LWA_SEG=32: 32 row segments per column (512 threads with up to 128 registers and twice the rows each)
+    // instead of 64 (1024 threads, 64 registers) -- A/B switch for the fp32 / 736-row instantiation
+    static const char* seg_env = getenv("XCB200_LWA_SEG");
+    if (seg_env && atoi(seg_env) == 32 && q_dtype == XC_F32 && cap == 736)
+        return increase ? go(k_lwa_cols<float, true, 736, 32>, (const float*)q, 32 * LC_TC)
+                        : go(k_lwa_cols<float, false, 736, 32>, (const float*)q, 32 * LC_TC);
+#define XC_LC_GO(QT, CAP) (increase ? go(k_lwa_cols<QT, true, CAP, 64>, (const QT*)q, 64 * LC_TC) : go(k_lwa_cols<QT, false, CAP, 64>, (const QT*)q, 64 * LC_TC))
     if (q_dtype == XC_F32) return cap == 256 ? XC_LC_GO(float, 256) : cap == 512 ? XC_LC_GO(float, 512) : XC_LC_GO(float, 736);
     return cap == 256 ? XC_LC_GO(double, 256) : cap == 512 ? XC_LC_GO(double, 512) : XC_LC_GO(double, 736);
 #undef XC_LC_GO
