@@ -63,6 +63,19 @@ def synth_slice_np(idx, lat, lon):
             + 0.02 * rng.standard_normal((NY, NX))).astype(np.float32)
 
 
+def nccl_options():
+    """One CTA per NCCL collective: the only collective of the path is a 1.7 MB all-gather per step that runs
+    beside the persistent LWA grid (one CTA per SM) -- it needs latency hiding, not SMs."""
+    try:
+        import torch.distributed as dist
+        o = dist.ProcessGroupNCCL.Options()
+        o.config.min_ctas = 1
+        o.config.max_ctas = 1
+        return o
+    except Exception:
+        return None
+
+
 def peak_hbm():
     try:
         return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
@@ -390,7 +403,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     ops.require_cuda()
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=nccl_options())
     dev = torch.device("cuda", local_rank)
     lat, lon = grid()
     dA = latlon_cell_area(lat, lon).astype(np.float32)

@@ -30,7 +30,7 @@ def main():
     dev = torch.device("cuda", lr)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev, pg_options=bench.nccl_options())
     lat, lon = bench.grid()
     dA = latlon_cell_area(lat, lon).astype(np.float32)
     plan = KeffLwaPlan(lat, lon, dA, bench.NLEV, increase=True, lt=True)
@@ -54,7 +54,7 @@ def main():
     outs = [plan.alloc_outputs(B) for _ in range(2)]
     ws = torch.empty(plan.workspace_bytes(B), dtype=torch.uint8, device=dev)
     gather = ContourGather(B, bench.NLEV, dev, nbuf=2) if world > 1 else None
-    tot_area = float(dA.astype(np.float64).sum())
+    tot_area = float(dA.astype(np.float64).sum()); max_cell = float(dA.max())
     acc = torch.zeros(8, dtype=torch.float64, device=dev)       # area_last, sum nkeff, sum lwa, min lwa, violations ...
     acc[3] = float("inf")
     t_gen = t_run = 0.0
@@ -84,7 +84,9 @@ def main():
             acc[3] = torch.minimum(acc[3], o["lwa"][:n].min())
             acc[4] += (o["area"][:n].diff(dim=1) < 0).sum() + (o["intgrdS"][:n].diff(dim=1) < 0).sum() \
                 + (o["Qref"][:n].diff(dim=1) < 0).sum()
-            acc[5] += ((o["area"][:n, -1] - tot_area).abs() > 1e-9 * tot_area).sum()
+            # area[-1] = sum dA, up to the cells that hold the slice maximum: the last level is the fp32-rounded
+            # end of the linspace and can sit one ulp below the maximum, which then falls outside
+            acc[5] += ((o["area"][:n, -1] - tot_area).abs() > 4.0 * max_cell).sum()
             acc[6] = torch.maximum(acc[6], o["lwa"][:n].max())
         e[3].record()
         torch.cuda.synchronize()
@@ -106,7 +108,7 @@ def main():
             "wall_s": tt[0], "slices_per_s_wall_incl_generation_and_checks": S / tt[0],
             "device_s_fused_batch_plus_gather": tt[2], "slices_per_s_fused_batch_plus_gather": S / tt[2],
             "device_s_generation": tt[1],
-            "invariants": {"non_monotone_cdf_or_Q_entries": red[3], "slices_with_area_last_off_by_1e-9": red[4],
+            "invariants": {"non_monotone_cdf_or_Q_entries": red[3], "slices_with_area_last_off_by_more_than_4_cells": red[4],
                            "lwa_min": float(mn), "lwa_max": float(mx)},
             "checksums": {"sum_area_last": red[0], "sum_nkeff": red[1], "sum_lwa": red[2]},
             "gather": None if gather is None else {"bytes_per_batch_per_gpu": int(outs[0].packed.nbytes), "batches": nb},
