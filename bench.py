@@ -64,16 +64,10 @@ def synth_slice_np(idx, lat, lon):
 
 
 def nccl_options():
-    """One CTA per NCCL collective: the only collective of the path is a 1.7 MB all-gather per step that runs
-    beside the persistent LWA grid (one CTA per SM) -- it needs latency hiding, not SMs."""
-    try:
-        import torch.distributed as dist
-        o = dist.ProcessGroupNCCL.Options()
-        o.config.min_ctas = 1
-        o.config.max_ctas = 1
-        return o
-    except Exception:
-        return None
+    """Default NCCL configuration.  (A one-CTA configuration was tried for the gather and measured at N = 8: the
+    collective then holds one SM for ~1.5 ms, and the persistent LWA grid -- one CTA per SM, static tile partition --
+    waits for that SM: 330 k instead of 660 k slices/s.  What the gather needs is to be short and rare.)"""
+    return None
 
 
 def peak_hbm():
@@ -419,25 +413,47 @@ def run_ours(args, rank, world, local_rank):
         phase = 2 * np.pi * torch.rand((), generator=g, device=dev, dtype=torch.float64)
         noise = torch.randn((NY, NX), generator=g, device=dev, dtype=torch.float32)
         q[s] = (torch.sin(phi) + 0.3 * torch.cos(phi) ** 2 * torch.sin(6 * lam + 3 * phi + phase)).float() + 0.02 * noise
-    # two output sets: with more than one GPU the contour-space results of step i are all-gathered on a side
-    # stream while step i+1 computes into the other set (the only collective of the path)
-    outs = [plan.alloc_outputs(B), plan.alloc_outputs(B)] if world > 1 else [plan.alloc_outputs(B)]
-    out = outs[0]
+    # Contour-space results are gathered across ranks every G steps (the only collective of the path):
+    # G consecutive steps write their [9, B, N] results into slabs of one packed buffer [9, G*B, N]; two such buffers
+    # alternate, so the all-gather of one (NCCL, side stream) overlaps the next G steps.  One larger collective every
+    # few steps instead of a small one per step: the NCCL kernel needs SMs, and the persistent LWA grid (one CTA per
+    # SM, all registers) cannot start on an SM that is busy with it.
+    G = max(1, args.gather_every) if world > 1 else 1
+    nset = 2 if world > 1 else 1
+    packs = [torch.empty((9, G * B, NLEV), dtype=torch.float64, device=dev) for _ in range(nset)]
+    lwa_buf = torch.empty((B, NY, NX), dtype=torch.float64, device=dev)
+    qref_buf = torch.empty((B, NY), dtype=torch.float64, device=dev)
+
+    def slab_outputs(pack, k):
+        from xcontour_b200.pipeline import CONTOUR_VARS, Outputs
+        o = Outputs((name, pack[i, k * B:(k + 1) * B]) for i, name in enumerate(CONTOUR_VARS))
+        o["Qref"], o["lwa"] = qref_buf, lwa_buf
+        return o
+    outs = [[slab_outputs(p, k) for k in range(G)] for p in packs]
+    out = outs[0][0]
     ws = torch.empty(plan.workspace_bytes(B), dtype=torch.uint8, device=dev)
-    gather = ContourGather(B, NLEV, dev, nbuf=2) if world > 1 else None
+    gather = ContourGather(G * B, NLEV, dev, nbuf=2) if world > 1 else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    pack_ev = [None] * nset                                  # completion of the last gather that read pack g
+    last = {"recv": None, "pack": 0}
+
+    def launch_gather(g):
+        recv, idx = gather.launch(packs[g])
+        pack_ev[g] = gather.event(idx)
+        last["recv"], last["pack"] = recv, g
+
     def step(i):
-        o = outs[i % len(outs)]
-        if gather is not None and i >= len(outs):          # the gather that last read this set must be done
-            torch.cuda.current_stream().wait_event(gather.event(i % 2))
-        plan.run(q, out=o, ws=ws)
-        if gather is not None:
-            gather.launch(o.packed)
+        g, k = (i // G) % nset, i % G
+        if gather is not None and k == 0 and pack_ev[g] is not None:     # the gather that last read this buffer must be done
+            torch.cuda.current_stream().wait_event(pack_ev[g])
+        plan.run(q, out=outs[g][k], ws=ws)
+        if gather is not None and k == G - 1:
+            launch_gather(g)
 
     def timed_region():
         """W warm-up steps, then exactly K timed steps between barriers; returns
@@ -451,6 +467,10 @@ def run_ours(args, rank, world, local_rank):
             step(n_w)
             torch.cuda.synchronize()
             n_w += 1
+        if gather is not None:               # the collective is warmed up too (NCCL connects lazily on first use)
+            launch_gather(0)
+            gather.wait()
+            torch.cuda.synchronize()
         barrier()
         ops.reset_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -459,6 +479,8 @@ def run_ours(args, rank, world, local_rank):
         for i in range(args.steps):
             step(i)
         if gather is not None:
+            if args.steps % G:               # a trailing partial group is gathered too
+                launch_gather(((args.steps - 1) // G) % nset)
             gather.wait()                    # the timed region ends when the last gather has landed
         e1.record()
         barrier()
@@ -494,9 +516,8 @@ def run_ours(args, rank, world, local_rank):
     value = world * B * args.steps / (ms_max * 1e-3)
     gather_check = None
     if gather is not None:                   # the gathered block of this rank is what it computed
-        last = (args.steps - 1) % 2
-        mine = gather.recv[last][rank]
-        gather_check = bool(torch.equal(mine.nan_to_num(), outs[(args.steps - 1) % len(outs)].packed.nan_to_num()))
+        torch.cuda.synchronize()
+        gather_check = bool(torch.equal(last["recv"][rank].nan_to_num(), packs[last["pack"]].nan_to_num()))
 
     # per-stage device time, CUDA events on the launching stream inside the same call
     stage = (ctypes.c_float * N_STAGES)()
@@ -573,8 +594,8 @@ def run_ours(args, rank, world, local_rank):
                              % (B * P * 4 / 1e6, B * P * 8 / 1e6),
                        "parallelism": ("slices sharded over %d GPU(s); " % world) +
                                       ("no collective at N=1" if world == 1 else
-                                       "the [9, B, N] contour-space results of every step are all-gathered (NCCL, side stream) "
-                                       "INSIDE the timed region")},
+                                       "the contour-space results of every step are all-gathered (NCCL, side stream, one [9, %d*B, N] "
+                                       "buffer every %d steps) INSIDE the timed region" % (G, G))},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": traffic,
                          "traffic_note": "ncu dram__bytes_read+write of one launch = one pass of 32 slices "
@@ -598,7 +619,8 @@ def run_ours(args, rank, world, local_rank):
         if c2d is not None:
             line["e2e_contour2d"] = c2d
         if gather is not None:
-            line["gather"] = {"in_timed_region": True, "bytes_per_step_per_gpu": int(outs[0].packed.nbytes),
+            line["gather"] = {"in_timed_region": True, "bytes_per_step_per_gpu": int(packs[0].nbytes) // G,
+                              "steps_per_collective": G, "collectives_in_timed_region": (args.steps + G - 1) // G,
                               "own_block_bit_identical": gather_check}
         if not args.no_cpu:
             v, cores, sample, legs = cpu_sample(nrows=96, per_core=3 if world == 1 else 1)
@@ -620,6 +642,7 @@ def main():
     ap.add_argument("--sub-batch", type=int, default=0, help="slices per internal pass (0 = auto)")
     ap.add_argument("--e2e-batch", type=int, default=8)
     ap.add_argument("--e2e-nbuf", type=int, default=2, help="batches in flight in the end-to-end leg")
+    ap.add_argument("--gather-every", type=int, default=5, help="steps per all-gather of the contour-space results (N > 1)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-api", action="store_true", help="skip the Contour2D-API end-to-end leg")
     ap.add_argument("--config", default="c4", choices=["c4", "c5"], help="BASELINE.json config 4 (default, the headline) or 5")
