@@ -415,9 +415,12 @@ def run_ours(args, rank, world, local_rank):
         q[s] = (torch.sin(phi) + 0.3 * torch.cos(phi) ** 2 * torch.sin(6 * lam + 3 * phi + phase)).float() + 0.02 * noise
     # Contour-space results are gathered across ranks every G steps (the only collective of the path):
     # G consecutive steps write their [9, B, N] results into slabs of one packed buffer [9, G*B, N]; two such buffers
-    # alternate, so the all-gather of one (NCCL, side stream) overlaps the next G steps.  One larger collective every
-    # few steps instead of a small one per step: the NCCL kernel needs SMs, and the persistent LWA grid (one CTA per
-    # SM, all registers) cannot start on an SM that is busy with it.
+    # alternate, so the all-gather of one (NCCL, side stream) overlaps the next G steps.  Default G = 1, every step's
+    # results are gathered as soon as they exist.  The NCCL kernel needs SMs, and the persistent LWA grid (one CTA
+    # per SM, all registers) cannot start on an SM that is busy with it, so a collective costs about its own duration
+    # once per G steps; measured (profiles/r2_gather_cadence.txt): G = 1 and G = 5 are within 1 % of each other at
+    # N = 4 (0.785 / 0.790 ms per step) and G = 1 is the better one at N = 8 (0.784 / 0.803), where the larger
+    # trailing collective of G = 5 is exposed at the end of the timed region.
     G = max(1, args.gather_every) if world > 1 else 1
     nset = 2 if world > 1 else 1
     packs = [torch.empty((9, G * B, NLEV), dtype=torch.float64, device=dev) for _ in range(nset)]
@@ -594,8 +597,8 @@ def run_ours(args, rank, world, local_rank):
                              % (B * P * 4 / 1e6, B * P * 8 / 1e6),
                        "parallelism": ("slices sharded over %d GPU(s); " % world) +
                                       ("no collective at N=1" if world == 1 else
-                                       "the contour-space results of every step are all-gathered (NCCL, side stream, one [9, %d*B, N] "
-                                       "buffer every %d steps) INSIDE the timed region" % (G, G))},
+                                       "the [9, B, N] contour-space results of every step are all-gathered (NCCL, side stream, "
+                                       "one collective per %s) INSIDE the timed region" % ("step" if G == 1 else "%d steps" % G))},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": traffic,
                          "traffic_note": "ncu dram__bytes_read+write of one launch = one pass of 32 slices "
@@ -642,7 +645,7 @@ def main():
     ap.add_argument("--sub-batch", type=int, default=0, help="slices per internal pass (0 = auto)")
     ap.add_argument("--e2e-batch", type=int, default=8)
     ap.add_argument("--e2e-nbuf", type=int, default=2, help="batches in flight in the end-to-end leg")
-    ap.add_argument("--gather-every", type=int, default=5, help="steps per all-gather of the contour-space results (N > 1)")
+    ap.add_argument("--gather-every", type=int, default=1, help="steps per all-gather of the contour-space results (N > 1)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-api", action="store_true", help="skip the Contour2D-API end-to-end leg")
     ap.add_argument("--config", default="c4", choices=["c4", "c5"], help="BASELINE.json config 4 (default, the headline) or 5")

@@ -414,3 +414,30 @@ def test_lwa_f32_opt_in_is_the_fp64_field_rounded_once(ops):
     for k in a:
         if k != "lwa":
             assert torch.equal(a[k].nan_to_num(), b[k].nan_to_num()), k
+
+
+# ---------------------------------------------------------------- lead dims paired by name (xarray's broadcasting)
+def test_interp_to_coords_pairs_slices_by_dimension_name(ops, vort):
+    """eqCoords (time, contour) against var (lev, time, contour): apply_ufunc (core.py:1089-1097) broadcasts by name,
+    so every (time, lev) slice of var is interpolated with the eqCoords row of ITS time; result dims (time, lev, new).
+    A second var whose lead sizes cannot be paired with eqCoords raises."""
+    import xcontour_b200 as xb
+    lat, lon, q = vort
+    tr = xb.DataArray(q[::8, ::8].copy(), dims=("latitude", "longitude"),
+                      coords={"latitude": lat[::8].copy(), "longitude": lon[::8].copy()}, name="pv")
+    an = xb.Contour2D(tr, tr, dims={"X": "longitude", "Y": "latitude"}, dimEq={"Y": "latitude"})
+    rng = np.random.default_rng(11)
+    T, L, N, M = 3, 2, 17, 9
+    e = np.sort(rng.random((T, N)) * 90.0, axis=-1)
+    v = rng.standard_normal((L, T, N))
+    pre = np.linspace(-5.0, 95.0, M)
+    ex = xb.DataArray(e, dims=("time", "contour"), coords={"time": np.arange(T)}, name="latEq")
+    vx = xb.DataArray(v, dims=("lev", "time", "contour"), coords={"lev": np.array([850.0, 500.0])}, name="v")
+    out = an.interp_to_coords(pre, ex, vx)
+    assert out.dims == ("time", "lev", "new") and out.shape == (T, L, M) and out.name == "v"
+    assert np.array_equal(out["lev"].values, [850.0, 500.0]) and np.array_equal(out["new"].values, pre)
+    for t in range(T):
+        for l in range(L):
+            assert np.array_equal(out.values[t, l], O.interp1d(pre, e[t], v[l, t], True))
+    with pytest.raises(Exception, match="cannot align"):
+        an.interp_to_coords(pre, ex, xb.DataArray(rng.random((T + 1, N)), dims=("time", "contour"), name="w"))

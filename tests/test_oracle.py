@@ -329,3 +329,28 @@ def test_workspace_planning_terminates_for_every_benchmark_shape():
     for args in ((1, 4096, 8192, 2048), (4, 4096, 8192, 2048), (32, 721, 1440, 361), (64, 721, 1440, 361),
                  (3, 83, 152, 47), (1, 8, 8, 2048), (5, 2, 8, 4), (100000, 721, 1440, 361)):
         assert lib.xc_keff_lwa_batch_workspace_bytes(*args) > 0
+
+
+def test_lead_dims_are_paired_by_name_not_by_position():
+    """interp_to_coords / cal_gradient_wrt_area pair slices the way xarray broadcasts them (core.py:1089-1097 runs
+    through apply_ufunc): by dimension name, union of the lead dims in order of first appearance."""
+    from xcontour_b200 import DataArray
+    from xcontour_b200.core import Contour2D
+    rng = np.random.default_rng(3)
+    T, L, N = 3, 2, 5
+    e = DataArray(rng.random((T, N)), dims=('time', 'contour'), coords={'time': np.arange(T)})
+    v = DataArray(rng.random((L, T, N)), dims=('lev', 'time', 'contour'), coords={'lev': [10., 20.]})
+    e2, v2, lead, lshape = Contour2D._align2(e, v)
+    assert lead == ['time', 'lev'] and lshape == (T, L)
+    assert e2.shape == (T * L, N) and v2.shape == (T * L, N)
+    for t in range(T):
+        for l in range(L):
+            assert np.array_equal(e2[t * L + l], e.values[t])          # repeated along the dim it lacks
+            assert np.array_equal(v2[t * L + l], v.values[l, t])       # transposed into the common order
+    # same sizes, different dim order: positions would pair the wrong slices
+    a = DataArray(rng.random((2, 2, N)), dims=('time', 'lev', 'contour'))
+    b = DataArray(rng.random((2, 2, N)), dims=('lev', 'time', 'contour'))
+    a2, b2, lead, _ = Contour2D._align2(a, b)
+    assert lead == ['time', 'lev'] and np.array_equal(b2[1], b.values[1, 0]) and np.array_equal(a2[1], a.values[0, 1])
+    with pytest.raises(Exception, match="cannot align"):
+        Contour2D._align2(e, DataArray(rng.random((T + 1, N)), dims=('time', 'contour')))

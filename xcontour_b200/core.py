@@ -447,12 +447,42 @@ class Contour2D(object):
         vals = np.transpose(vals, [da.dims.index(d) for d in lead + [interp_dim]])
         return vals.reshape(-1, vals.shape[-1]), lead, vals.shape[:-1]
 
+    @staticmethod
+    def _align2(a, b, interp_dim='contour'):
+        """
+        Two labelled operands as [S, n_a] and [S, n_b] arrays with ``interp_dim`` last and the other dims paired BY
+        NAME, as xarray broadcasts them (the reference runs these steps through DataArray arithmetic / apply_ufunc):
+        the lead dims are the union in order of first appearance, an operand that lacks one is repeated along it,
+        and a dim present in both with different lengths is an error.  Returns (a2, b2, lead dims, lead shape).
+        """
+        la = [d for d in a.dims if d != interp_dim]
+        lb = [d for d in b.dims if d != interp_dim]
+        lead = la + [d for d in lb if d not in la]
+        size = {}
+        for arr in (a, b):
+            for d, n in zip(arr.dims, arr.shape):
+                if d == interp_dim:
+                    continue
+                if size.setdefault(d, n) != n:
+                    raise Exception('cannot align dimension %r: sizes %d and %d' % (d, size[d], n))
+        lshape = tuple(size[d] for d in lead)
+
+        def flat(arr, own):
+            vals = np.asarray(arr.values)
+            order = [d for d in lead if d in own] + [interp_dim]
+            vals = np.transpose(vals, [arr.dims.index(d) for d in order])
+            n = vals.shape[-1]
+            vals = vals.reshape(tuple(size[d] if d in own else 1 for d in lead) + (n,))
+            if vals.shape[:-1] != lshape:
+                vals = np.broadcast_to(vals, lshape + (n,))
+            return np.ascontiguousarray(vals).reshape(-1, n)
+        return flat(a, la), flat(b, lb), lead, lshape
+
     def cal_gradient_wrt_area(self, var, area):
         """d(var)/dA by centred differences along the contour axis (core.py:463-488)."""
-        v, lead, lshape = self._flat2(var)
-        a, _, _ = self._flat2(area)
+        v, a, lead, lshape = self._align2(var, area)
         if a.shape != v.shape:
-            a = np.broadcast_to(a, v.shape)
+            raise Exception('var and area differ along contour: %d and %d' % (v.shape[-1], a.shape[-1]))
         vt, at = ops.as_float(ops.to_dev(v)), ops.as_float(ops.to_dev(a))
         # differentiate('contour') runs against each array's own 'contour' coordinate: 0..N-1 from cal_contours(int),
         # the level values themselves after cal_contours(array) (core.py:253-264), possibly non-uniform
@@ -468,7 +498,8 @@ class Contour2D(object):
         if rdt not in (np.float32, np.float64):
             rdt = np.float64
         res = out.cpu().numpy().astype(rdt).reshape(tuple(lshape) + (v.shape[-1],))
-        coords = xc.coords_for(var, lead + ['contour'])
+        coords = xc.coords_for(area, [d for d in lead if d in area.dims])
+        coords.update(xc.coords_for(var, [d for d in lead + ['contour'] if d in var.dims]))
         name = 'dvardA' if var.name is None else 'd' + var.name + 'dA'
         return xc.make(res, lead + ['contour'], coords, name)
 
@@ -617,17 +648,16 @@ class Contour2D(object):
         else:
             dimTmp = predef.dims[0]
             pvals = np.asarray(predef.values)
-        e, elead, eshape = self._flat2(eqCoords, interpDim)
-        v, vlead, vshape = self._flat2(var, interpDim)
+        # slices are paired by dimension name (apply_ufunc's broadcasting), eqCoords' dims first
+        e, v, lead, lshape = self._align2(eqCoords, var, interpDim)
         increasing = bool(e[0, 0] < e[0, -1])                   # core.py:1080-1088
-        lead, lshape = (elead, eshape) if len(elead) >= len(vlead) else (vlead, vshape)
         et = ops.to_dev(e.astype(np.float64))
         vt = ops.to_dev(v.astype(np.float64))
         out = ops.interp(ops.to_dev(pvals.astype(np.float64)), et if e.shape[0] > 1 else et[0],
                          vt if v.shape[0] > 1 else vt[0], reverse=0 if increasing else 1)
         res = out.cpu().numpy().reshape(tuple(lshape) + (pvals.shape[0],))
-        src = eqCoords if len(elead) >= len(vlead) else var
-        coords = xc.coords_for(src, lead)
+        coords = xc.coords_for(var, [d for d in lead if d in var.dims])
+        coords.update(xc.coords_for(eqCoords, [d for d in lead if d in eqCoords.dims]))
         coords[dimTmp] = pvals
         return xc.make(res, lead + [dimTmp], coords, var.name)
 

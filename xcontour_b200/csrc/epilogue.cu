@@ -37,7 +37,7 @@ struct EpiParams {
     int32_t* sorted; int32_t* any_unsorted;
 };
 
-__global__ void __launch_bounds__(256) k_scan_epilogue(const EpiParams p)
+__global__ void __launch_bounds__(1024) k_scan_epilogue(const EpiParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int N = p.N;
@@ -73,8 +73,8 @@ __global__ void __launch_bounds__(256) k_scan_epilogue(const EpiParams p)
     // sequential running sums, exactly np.cumsum's order (core.py:1320): empty bins
     // leave the CDFs bit-for-bit flat (so d/dA sees exact zeros where the reference
     // does); the two accumulators are scanned by two different warps at once
-    if (tid == 0)  { double run = 0.0; for (int r = 0; r < N; ++r) { run += sa[r]; sa[r] = run; } }
-    if (tid == 32) { double run = 0.0; for (int r = 0; r < N; ++r) { run += sg[r]; sg[r] = run; } }
+    if (tid == 0)  serial_cumsum(sa, N);
+    if (tid == 32) serial_cumsum(sg, N);
     __syncthreads();
     // cdf[-1] - cdf for the 'greater than' case (core.py:1322-1323), then the flip
     // that makes the contour index ascend (core.py:454-455) -- both in place
@@ -184,7 +184,10 @@ int xc::scan_epilogue(const double* part, int C, long S, int N, int lt, const in
     XC_REQUIRE(sm <= 200 * 1024, "xc_keff_lwa_batch: N too large for the fused epilogue");
     if (sm > 48 * 1024)
         XC_CUDA_OK(cudaFuncSetAttribute(k_scan_epilogue, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_scan_epilogue<<<(unsigned)S, 256, sm, (cudaStream_t)stream>>>(p);
+    // one CTA per slice: 256 threads cover config 4's 361 levels / 721 rows in two or three rounds; many levels or
+    // rows (config 5: 2048 / 4096) get 1024
+    const unsigned nt = (N > 512 || ny > 1024 || n_table > 1024) ? 1024u : 256u;
+    k_scan_epilogue<<<(unsigned)S, nt, sm, (cudaStream_t)stream>>>(p);
     XC_LAUNCH_OK();
     return 0;
 }

@@ -381,10 +381,7 @@ k_reduce_scan(const double* __restrict__ part, int C, int K, int N, int scan_mod
     // leave the CDF bit-for-bit flat and the CDF of non-negative weights is monotone,
     // which the d/dA step and check_mono rely on.  N additions by one thread cost a
     // few microseconds; the parallelism of this kernel is across (slice, accumulator).
-    if (tid == 0) {
-        double run = 0.0;
-        for (int r = 0; r < N; ++r) { run += pd[r]; pd[r] = run; }
-    }
+    if (tid == 0) serial_cumsum(pd, N);
     __syncthreads();
     if (tid == 0) total_s = pd[N - 1];
     __syncthreads();

@@ -142,6 +142,8 @@ def interp(x, xp, fp, reverse=-1):
             fp.shape[0] if fp.dim() == 2 else 1)
 
     def st(t, last):
+        if t.dim() == 2 and t.shape[0] not in (1, S):
+            raise Exception("interp: operands with %d and %d slices cannot be paired" % (t.shape[0], S))
         return last if (t.dim() == 2 and t.shape[0] == S) else 0
     out = torch.empty((S, M), dtype=torch.float64, device=x.device)
     check(lib.xc_interp(_p(x), st(x, M), M, _p(xp), st(xp, n), _p(fp), st(fp, n), n, int(reverse),
