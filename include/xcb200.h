@@ -234,8 +234,8 @@ int xc_latlon_cell_area(const double* lat_deg, int n_y, int n_x, double dlambda_
  * Qref: [S][n_y] fp64;  lwa: [S][n_y][n_x] fp64.
  * grdS: [S][P] (dtype grdS_dtype) or NULL -> computed in flight from q with the
  * stencil of (7) inside the binning kernel and never written to HBM.
- * The batch is walked in passes of `sub_batch` slices so that the three reads of
- * a slice (min/max, binning, LWA) after the first are served by the 126 MB L2.
+ * The batch is walked in passes of `sub_batch` slices (32 at 721x1440), two passes in flight on internal
+ * streams.  A slice is read from HBM once per stage (min/max, binning, LWA): a pass does not fit the 126 MB L2.
  * ---------------------------------------------------------------------- */
 typedef struct xc_keff_lwa_args {
     const void*   q;          int q_dtype;
@@ -250,7 +250,7 @@ typedef struct xc_keff_lwa_args {
     const double* ww;         /* [n_y][n_x] from xc_lwa_weights */
     double        keff_mask;  /* cal_normalized_Keff(mask=...) */
     int           part;
-    int           sub_batch;  /* slices per internal pass; 0 = auto (one pass's q + LWA stay L2-resident) */
+    int           sub_batch;  /* slices per internal pass; 0 = auto (~400 MB of q + LWA per pass) */
     double *ctr, *area, *intgrdS, *latEq, *Lmin, *dintSdA, *dqdA, *Leq2, *nkeff;
     double *Qref, *lwa;
     /* optional HOST pointer to XC_N_STAGES floats: per-stage device time in ms
@@ -274,6 +274,11 @@ typedef struct xc_keff_lwa_args {
     /* opt-in, NOT a drop-in result: lwa points to [S][n_y][n_x] fp32 and receives the fp64 result rounded once
      * (halves the bytes of the largest output; needs ww_row and n_y <= 768) */
     int           lwa_f32;
+    /* ---- ABI version 3 ---- */
+    /* NumPy scalar-promotion regime of the reference's per-'time' bin edges (core.py:1273-1281): 0 = NumPy 1.x
+     * (step and edges promoted to fp64, as xc_hist_edges with time_branch = 1), 1 = NEP 50 / NumPy >= 2 (the edge
+     * array keeps the contour dtype, as time_branch = 0).  Only the first and last edge differ. */
+    int           numpy2_rules;
 } xc_keff_lwa_args;
 #define XC_N_STAGES 5
 

@@ -34,9 +34,9 @@ Parity status
   ``squared_gradient_latlon``, which has no counterpart in the reference.
 * NumPy regime: the reference was written for NumPy 1.x.  Its scalar-promotion rules
   differ from NEP 50 (NumPy >= 2) in one place on this path, the fp64 ``step`` of
-  ``_histogram`` (see ``hist_edges``); ``scalar_rules="numpy1"`` (default, and what the
-  CUDA path implements by default) and ``"numpy2"`` (the regime the fixtures were
-  generated in; ``XCB200_NUMPY_RULES=numpy2`` in the product) restate both.
+  ``_histogram`` (see ``hist_edges``); ``scalar_rules="numpy1"`` (the default here) and
+  ``"numpy2"`` (the regime the fixtures were generated in) restate both.  The CUDA path
+  implements both and follows the installed NumPy unless ``XCB200_NUMPY_RULES`` says otherwise.
 
 Array conventions: a tracer is ``q[S, n0, n1]`` (S independent slices, the 2-D
 plane last); contour-space arrays are ``[S, N]``; ``dA`` is ``[n0, n1]``.

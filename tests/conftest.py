@@ -15,6 +15,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+@pytest.fixture(autouse=True)
+def _oracle_default_scalar_rules(monkeypatch):
+    """The oracle's functions default to scalar_rules="numpy1" (the NumPy the reference documents); the product
+    defaults to the regime of the installed NumPy.  Tests compare the two under one stated regime: numpy1 unless a
+    test selects the other itself (the reference-run fixtures, the numpy2 tests)."""
+    from xcontour_b200 import utils
+    monkeypatch.setattr(utils, "NUMPY_SCALAR_RULES", "numpy1")
+
+
 @pytest.fixture(scope="session")
 def vort():
     """lat[256], lon[512], absolute_vorticity[256,512] of the reference's

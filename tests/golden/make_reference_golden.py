@@ -22,8 +22,8 @@ in one place on this path -- ``step = (c_last - c_first)/(len-1)`` of
 ``_histogram`` (core.py:1277, 1300) is fp32 under NEP 50 and fp64 under the 1.x
 rules, which decides the dtype of the per-'time' edge array (core.py:1278) and hence
 whether xhistogram's ``+1e-8`` nudge of the last edge is a no-op.  The oracle restates
-both (``scalar_rules="numpy1"`` -- its default, what the CUDA path implements -- and
-``"numpy2"``); the fixture tests select the regime recorded in each file.
+both (``scalar_rules="numpy1"`` -- its default -- and ``"numpy2"``), the CUDA path implements both and follows the
+installed NumPy by default; the fixture tests select the regime recorded in each file.
 
 Cases
 -----

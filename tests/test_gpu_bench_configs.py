@@ -441,3 +441,42 @@ def test_interp_to_coords_pairs_slices_by_dimension_name(ops, vort):
             assert np.array_equal(out.values[t, l], O.interp1d(pre, e[t], v[l, t], True))
     with pytest.raises(Exception, match="cannot align"):
         an.interp_to_coords(pre, ex, xb.DataArray(rng.random((T + 1, N)), dims=("time", "contour"), name="w"))
+
+
+# ---------------------------------------------------------------- NumPy regime of the per-'time' edges, fused path
+@pytest.mark.parametrize("increase,lt", [(True, True), (False, False), (True, False)])
+def test_fused_batch_in_both_numpy_regimes(ops, increase, lt):
+    """core.py:1273-1281 builds the per-'time' edges with NumPy scalars: fp64 edges under NumPy 1.x, fp32 under
+    NEP 50.  xc_keff_lwa_batch (ABI 3: numpy2_rules) reproduces either; each is held to the oracle's statement of
+    the same regime, and the Contour2D hist path agrees with the fused path in both."""
+    import xcontour_b200 as xb
+    from xcontour_b200 import utils as xutils
+    from xcontour_b200.pipeline import KeffLwaPlan
+    lat, lon, q = synth_c4(3, 91, 180)
+    dA = O.latlon_cell_area(lat, lon).astype(np.float32)
+    N = 41
+    ctr = O.cal_contours(q, N, increase)
+    grd = O.squared_gradient_latlon(q, lat, lon)
+    areas = {}
+    for rules in ("numpy1", "numpy2"):
+        plan = KeffLwaPlan(lat, lon, dA, N, increase=increase, lt=lt, scalar_rules=rules)
+        out = plan.run(torch.as_tensor(q, device="cuda"))
+        torch.cuda.synchronize()
+        ref_a = O.cal_integral_within_contours_hist(q, ctr, dA, lt, scalar_rules=rules)
+        ref_g = O.cal_integral_within_contours_hist(q, ctr, dA, lt, integrand=grd, scalar_rules=rules)
+        assert np.array_equal(out["ctr"].cpu().numpy().astype(np.float32), ctr)
+        assert relmax(out["area"].cpu().numpy(), ref_a) <= RTOL_INT
+        assert relmax(out["intgrdS"].cpu().numpy(), ref_g) <= 1e-11
+        areas[rules] = out["area"].cpu().numpy()
+        # the drop-in API in the same regime
+        xutils.NUMPY_SCALAR_RULES = rules                           # (restored by the autouse fixture's monkeypatch)
+        coords = {"time": np.arange(3), "latitude": lat, "longitude": lon}
+        tr = xb.DataArray(q, dims=("time", "latitude", "longitude"), coords=coords, name="q")
+        an = xb.Contour2D(tr, xb.DataArray(dA, dims=("latitude", "longitude")), dims={"X": "longitude", "Y": "latitude"},
+                          dimEq={"Y": "latitude"}, increase=increase, lt=lt)
+        a_api = an.cal_integral_within_contours_hist(an.cal_contours(N))
+        assert relmax(a_api.values, areas[rules]) <= RTOL_INT          # (general kernel: fp64 partial sums)
+    # the regimes differ exactly where the reference's do (the cell that holds the maximum, last-edge nudge)
+    ref1 = O.cal_integral_within_contours_hist(q, ctr, dA, lt, scalar_rules="numpy1")
+    ref2 = O.cal_integral_within_contours_hist(q, ctr, dA, lt, scalar_rules="numpy2")
+    assert np.array_equal(areas["numpy1"] != areas["numpy2"], ref1 != ref2)

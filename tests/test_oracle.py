@@ -179,7 +179,7 @@ def test_library_builds_and_exports_every_declared_symbol():
         assert hasattr(lib, s), "missing export %s" % s
     assert set(_lib.SIGNATURES) == set(syms)
     lib.xc_abi_version.restype = ctypes.c_int
-    assert lib.xc_abi_version() == 2
+    assert lib.xc_abi_version() == 3
 
 
 def test_size_queries_and_argument_errors_without_gpu():
@@ -354,3 +354,20 @@ def test_lead_dims_are_paired_by_name_not_by_position():
     assert lead == ['time', 'lev'] and np.array_equal(b2[1], b.values[1, 0]) and np.array_equal(a2[1], a.values[0, 1])
     with pytest.raises(Exception, match="cannot align"):
         Contour2D._align2(e, DataArray(rng.random((T + 1, N)), dims=('time', 'contour')))
+
+
+def test_default_scalar_rules_follow_the_installed_numpy():
+    """The per-'time' bin edges of _histogram depend on NumPy's scalar promotion (core.py:1277-1278); by default the
+    product reproduces what the reference computes under the NumPy that is installed, and the switch is explicit."""
+    code = ("import numpy as np; from xcontour_b200 import utils; "
+            "print(utils.NUMPY_SCALAR_RULES, int(np.__version__.split('.')[0]))")
+    env = {k: v for k, v in os.environ.items() if k != "XCB200_NUMPY_RULES"}
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, check=True).stdout.split()
+    assert out[0] == ("numpy2" if int(out[1]) >= 2 else "numpy1")
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=dict(env, XCB200_NUMPY_RULES="numpy1"),
+                         capture_output=True, text=True, check=True).stdout.split()
+    assert out[0] == "numpy1"
+    from xcontour_b200 import utils
+    assert utils.scalar_rules("numpy2") == "numpy2" and utils.scalar_rules() == "numpy1"      # conftest pins numpy1
+    with pytest.raises(Exception, match="scalar rules"):
+        utils.scalar_rules("numpy3")

@@ -229,10 +229,10 @@ def test_product_matches_reference_fixtures(case, monkeypatch):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     import xcontour_b200 as xb
-    from xcontour_b200 import core as xcore
+    from xcontour_b200 import utils as xutils
     eq, lead, with_grd = CASES[case]
     fx = G.load(case)
-    monkeypatch.setattr(xcore, "NUMPY_SCALAR_RULES", str(fx["meta/scalar_rules"]))
+    monkeypatch.setattr(xutils, "NUMPY_SCALAR_RULES", str(fx["meta/scalar_rules"]))
     dims2 = (eq, "X")
     coords = {eq: fx["in/" + eq], "X": fx["in/X"]}
     dims_q, coords_q = (("time",) + dims2, dict(coords, time=fx["in/time"])) if lead else (dims2, coords)

@@ -44,6 +44,7 @@ class KeffLwaArgs(Structure):
         ("cx", c_void_p), ("cy", c_void_p), ("bcx", c_int), ("bcy", c_int), ("fill_value", c_double),
         ("dA_row", c_void_p), ("uniform_dA", c_int), ("any_degenerate", c_int),
         ("ww_row", c_void_p), ("lwa_f32", c_int),
+        ("numpy2_rules", c_int),
     ]
 
 

@@ -27,18 +27,14 @@ import numpy as np
 import torch
 
 from . import ops
+from . import utils
 from ._lib import (SCAN_PREFIX, SCAN_SUFFIX, SCAN_TOTAL_MINUS, XC_F32,
                    XC_F32_AS_F64, XC_F64)
 from . import xr_compat as xc
 from .xr_compat import DataArray, Dataset, merge
 
-# Which NumPy scalar-promotion regime of the reference is reproduced where the two
-# differ (hazard H4): under the NumPy-1.x rules the reference was written
-# for, `step` of _histogram (core.py:1277) is fp64 and the per-'time' edge array is
-# fp64 (core.py:1278), so xhistogram's +1e-8 closes the last bin over the maximum
-# cell; under NEP 50 (NumPy >= 2) the edges keep the contour dtype.  "numpy1" is the
-# default; XCB200_NUMPY_RULES=numpy2 (or assigning this variable) selects the other.
-NUMPY_SCALAR_RULES = os.environ.get("XCB200_NUMPY_RULES", "numpy1")
+# The NumPy scalar-promotion regime of the reference that is reproduced (numpy1 | numpy2) lives in
+# utils.NUMPY_SCALAR_RULES: by default the regime of the installed NumPy (hazard H4).
 
 
 def _np_dtype_code(dt):
@@ -331,7 +327,7 @@ class Contour2D(object):
         ctr_code = _np_dtype_code(levels.dtype) if levels.dtype in (np.float32, np.float64) \
             else XC_F64
         edges, decr = ops.hist_edges(ops.to_dev(levels.astype(np.float64)), ctr_code,
-                                     time_branch=per_slice and NUMPY_SCALAR_RULES != "numpy2")
+                                     time_branch=per_slice and utils.scalar_rules() != "numpy2")
         dA_dev, dA_np = self._dA_plane(plane, trc)
         integ = []
         if integrand is not None:

@@ -3,10 +3,12 @@
 // entries launch (same arithmetic, same parity); the intermediate contour-space
 // arrays live in the caller's workspace.  This is the call bench.py times.
 //
-// The batch is walked in passes of `sub` slices.  A slice is read three times
-// (min/max, binning + in-flight |grad q|^2, LWA); with a pass footprint of
-// sub * (q + LWA) well inside the 126 MB L2 only the first read and the LWA
-// store touch HBM, which is the algorithmic traffic of DESIGN.md.
+// The batch is walked in passes of `sub` slices, two passes in flight on internal
+// streams.  A slice is read three times (min/max, binning + in-flight |grad q|^2,
+// LWA), each time from HBM: a 32-slice pass (133 MB of q + 266 MB of LWA at 721x1440)
+// does not fit the 126 MB L2, and shorter passes measured slower (launch tails).  The
+// pipeline therefore moves ~20 MB per slice against 12.46 MB of algorithmic traffic
+// (profiles/traffic.json); each kernel is judged against its own compulsory bytes.
 #include "common.cuh"
 #include "internal.h"
 #include <stdlib.h>
@@ -187,7 +189,7 @@ extern "C" int xc_keff_lwa_batch(const xc_keff_lwa_args* a, void* workspace, siz
         mark(0);
         // (1)+(1b) min/max, levels and per-'time'-branch edges in two launches
         if (minmax_levels_impl(q, a->q_dtype, ns, P, N, a->increase, a->ctr_dtype, ctr, L.minmax,
-                               L.edges, L.decr, L.any_unsorted, L.w_minmax, pl.ws_minmax, ps)) return 1;
+                               L.edges, L.decr, L.any_unsorted, L.w_minmax, pl.ws_minmax, ps, a->numpy2_rules)) return 1;
         mark(1);
         mark(2);
         // (2) area and int |grad q|^2 dA in one pass over q (per-CTA partials only)

@@ -59,7 +59,8 @@ size_t bin_rows_part_doubles(long S, int ny, int nx, int N);
 // levels (+ optional per-'time'-branch edges in the same launch); clears *flag_to_clear
 int minmax_levels_impl(const void* q, int q_dtype, long S, long P, int N, int increase, int out_dtype,
                        double* levels, double* minmax, double* edges, int32_t* decreasing,
-                       int32_t* flag_to_clear, void* workspace, size_t ws_bytes, void* stream);
+                       int32_t* flag_to_clear, void* workspace, size_t ws_bytes, void* stream,
+                       int edges_keep_ctr_dtype = 0);
 
 // LWA with sortedness flags already on the device (fused path)
 // minmax: NaN-skipping (min, max) per slice [S][2] if the caller has them (else they are

@@ -193,7 +193,7 @@ __global__ void k_levels(const double* __restrict__ part, int C, int N, int incr
                          int q_is_f32, int out_is_f32,
                          double* __restrict__ levels, double* __restrict__ minmax,
                          double* __restrict__ edges, int32_t* __restrict__ decreasing,
-                         int32_t* __restrict__ flag_to_clear)
+                         int32_t* __restrict__ flag_to_clear, int edges_keep_ctr_dtype)
 {
     const long s = blockIdx.x;
     if (flag_to_clear && s == 0 && threadIdx.x == 0) *flag_to_clear = 0;
@@ -233,10 +233,12 @@ __global__ void k_levels(const double* __restrict__ part, int C, int N, int incr
         const double first = binc ? c0 : cl, last = binc ? cl : c0;
         const double d = out_is_f32 ? (double)__fsub_rn((float)last, (float)first) : __dsub_rn(last, first);
         const double step = __ddiv_rn(d, (double)(N - 1));
+        const bool e32 = out_is_f32 && edges_keep_ctr_dtype;    // NumPy >= 2 scalar rules: as k_hist_edges with time_branch = 0
         double* e = edges + s * (long)(N + 1);
         for (int k = threadIdx.x; k <= N; k += blockDim.x) {
             double v = (k == 0) ? __dsub_rn(first, step) : (binc ? level(k - 1) : level(N - k));
-            if (k == N) v = __dadd_rn(v, 1e-8);
+            if (k == 0 && e32) v = (double)__double2float_rn(v);
+            if (k == N) v = e32 ? (double)__fadd_rn((float)v, 1e-8f) : __dadd_rn(v, 1e-8);
             e[k] = v;
         }
         if (threadIdx.x == 0 && decreasing) decreasing[s] = binc ? 0 : 1;
@@ -303,12 +305,13 @@ extern "C" int xc_minmax_levels(const void* q, int q_dtype, long S, long P,
                                 void* workspace, size_t ws_bytes, void* stream)
 {
     return minmax_levels_impl(q, q_dtype, S, P, N, increase, out_dtype, levels, minmax,
-                              nullptr, nullptr, nullptr, workspace, ws_bytes, stream);
+                              nullptr, nullptr, nullptr, workspace, ws_bytes, stream, 0);
 }
 
 int xc::minmax_levels_impl(const void* q, int q_dtype, long S, long P, int N, int increase, int out_dtype,
                            double* levels, double* minmax, double* edges, int32_t* decreasing,
-                           int32_t* flag_to_clear, void* workspace, size_t ws_bytes, void* stream)
+                           int32_t* flag_to_clear, void* workspace, size_t ws_bytes, void* stream,
+                           int edges_keep_ctr_dtype)
 {
     XC_REQUIRE(q && levels, "xc_minmax_levels: null pointer");
     XC_REQUIRE(S > 0 && P > 0 && N >= 2, "xc_minmax_levels: need S>0, P>0, N>=2");
@@ -350,7 +353,8 @@ int xc::minmax_levels_impl(const void* q, int q_dtype, long S, long P, int N, in
         XC_LAUNCH_OK();
     }
     k_levels<<<(unsigned)S, 128, 0, st>>>(part, (int)C, N, increase, q_dtype == XC_F32,
-                                          out_dtype == XC_F32, levels, minmax, edges, decreasing, flag_to_clear);
+                                          out_dtype == XC_F32, levels, minmax, edges, decreasing, flag_to_clear,
+                                          edges_keep_ctr_dtype);
     XC_LAUNCH_OK();
     return 0;
 }

@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from . import _lib, ops
-from .utils import BOUNDARY, row_metrics_latlon
+from .utils import BOUNDARY, row_metrics_latlon, scalar_rules as _scalar_rules
 from ._lib import KeffLwaArgs, PART, SCAN_PREFIX, SCAN_TOTAL_MINUS, XC_F32, XC_F64, check
 
 CONTOUR_VARS = ("ctr", "area", "intgrdS", "latEq", "Lmin", "dintSdA", "dqdA", "Leq2", "nkeff")
@@ -49,11 +49,13 @@ class KeffLwaPlan(object):
 
     def __init__(self, lat_deg, lon_deg, dA, N, increase=True, lt=True,
                  dtype=np.float32, keff_mask=1e5, part="all", mask=None, sub_batch=0,
-                 metrics=None, boundary=("periodic", "extend"), fill_value=0.0):
+                 metrics=None, boundary=("periodic", "extend"), fill_value=0.0, scalar_rules=None):
         """lat_deg / lon_deg: the equivalent (row) coordinate and the column coordinate of the plane.
         metrics: (cx[ny], cy[ny]) row metrics of the |grad q|^2 stencil (utils.row_metrics_cartesian for
         Cartesian / X-Z planes); default: the lat-lon metrics of utils.row_metrics_latlon.
-        boundary: ghost-cell rule along (x, y), each one of utils.BOUNDARY; fill_value for 'fill'."""
+        boundary: ghost-cell rule along (x, y), each one of utils.BOUNDARY; fill_value for 'fill'.
+        scalar_rules: 'numpy1' | 'numpy2', the NumPy regime of the reference's per-'time' bin edges that is
+        reproduced (utils.NUMPY_SCALAR_RULES: the installed NumPy's by default)."""
         ops.require_cuda()
         lat = np.asarray(lat_deg)
         lon = np.asarray(lon_deg)
@@ -62,6 +64,7 @@ class KeffLwaPlan(object):
         self.ctr_dtype = XC_F32 if np.dtype(dtype) == np.float32 else XC_F64
         self.keff_mask, self.part = float(keff_mask), PART[part]
         self.sub_batch = int(sub_batch)
+        self.numpy2_rules = _scalar_rules(scalar_rules) == "numpy2"
         dA = np.ascontiguousarray(np.broadcast_to(np.asarray(dA), (self.ny, self.nx)))
         self.dA = ops.to_dev(dA)
         self.ww = ops.lwa_weights(self.dA.reshape(-1))
@@ -148,6 +151,7 @@ class KeffLwaPlan(object):
         a.Qref = out["Qref"].data_ptr() if "Qref" in out else None
         a.lwa = out["lwa"].data_ptr() if "lwa" in out else None
         a.lwa_f32 = int("lwa" in out and out["lwa"].dtype == torch.float32)
+        a.numpy2_rules = int(self.numpy2_rules)
         a.stage_ms = ctypes.cast(stage_ms, ctypes.c_void_p) if stage_ms is not None else None
         check(lib.xc_keff_lwa_batch(ctypes.byref(a), ctypes.c_void_p(ws.data_ptr()), nb, ops.stream_ptr()))
         return out

@@ -1,6 +1,8 @@
 """
 Sphere helpers of xcontour/utils.py:491-534 over the GPU element-wise kernels.
 """
+import os
+
 import numpy as np
 
 from . import ops
@@ -53,6 +55,30 @@ def latlon_cell_area(lat_deg, lon_deg, Rearth=Rearth):
         band = band[::-1]
     dlam = np.deg2rad(abs(lon[1] - lon[0]))
     return np.repeat((band * dlam)[:, None], len(lon), axis=1)
+
+
+# Which NumPy scalar-promotion regime of the reference is reproduced where the two differ (hazard H4):
+# under the NumPy-1.x rules the reference was written for, `step` of _histogram (core.py:1277) is fp64 and the
+# per-'time' edge array is fp64 (core.py:1278), so xhistogram's +1e-8 closes the last bin over the maximum cell; under
+# NEP 50 (NumPy >= 2) the edges keep the contour dtype.  The default is the regime of the NumPy that is installed --
+# what the reference itself would compute on this machine; XCB200_NUMPY_RULES=numpy1|numpy2 (or assigning this
+# variable) selects one explicitly.
+def _installed_numpy_rules():
+    try:
+        return "numpy2" if int(np.__version__.split(".")[0]) >= 2 else "numpy1"
+    except ValueError:
+        return "numpy1"
+
+
+NUMPY_SCALAR_RULES = os.environ.get("XCB200_NUMPY_RULES") or _installed_numpy_rules()
+
+
+def scalar_rules(rules=None):
+    """the regime in force: an explicit argument, else the module variable"""
+    r = NUMPY_SCALAR_RULES if rules is None else rules
+    if r not in ("numpy1", "numpy2"):
+        raise Exception("scalar rules should be 'numpy1' or 'numpy2', got %r" % (r,))
+    return r
 
 
 BOUNDARY = {"periodic": 0, "extend": 1, "reflect": 2, "fill": 3}   # XC_BC_* of include/xcb200.h
