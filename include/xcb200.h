@@ -286,6 +286,21 @@ size_t xc_keff_lwa_batch_workspace_bytes(long S, int n_y, int n_x, int N);
 int xc_keff_lwa_batch(const xc_keff_lwa_args* args,
                       void* workspace, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------
+ * (9) equal-area contour levels by a weighted-quantile histogram -- north_star kernel (1); an extension of the
+ * reference, which offers equally spaced levels (cal_contours, core.py:205-266) and levels at prescribed
+ * equivalent coordinates (cal_contours_at_hist, core.py:316-360).  One call on the device: min/max ->
+ * (N-1)*refine+1 equally spaced fine levels and their bin edges -> their area CDF by the histogram path of
+ * core.py:412-460 (lt: area where q < level, else q > level) -> the A(q) relation inverted by np.interp at N
+ * equally spaced areas -> rounded once to `out_dtype`.  levels: [S][N] fp64 holding the rounded values; adjacent
+ * levels enclose, to within one fine bin, the same area.  numpy2_rules: as in xc_keff_lwa_args.
+ * ---------------------------------------------------------------------- */
+size_t xc_equal_area_levels_workspace_bytes(long S, long P, int N, int refine);
+int xc_equal_area_levels(const void* q, int q_dtype, long S, long P,
+                         const void* dA, int dA_dtype,
+                         int N, int refine, int increase, int lt, int out_dtype, int numpy2_rules,
+                         double* levels, void* workspace, size_t ws_bytes, void* stream);
+
 /* number of kernel launches issued by this library on the calling thread since
  * the last xc_reset_launch_count() (bench.py reports it as gpu_launches). */
 long xc_launch_count(void);

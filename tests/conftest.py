@@ -15,13 +15,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
-@pytest.fixture(autouse=True)
-def _oracle_default_scalar_rules(monkeypatch):
+@pytest.fixture(autouse=True, scope="session")
+def _oracle_default_scalar_rules():
     """The oracle's functions default to scalar_rules="numpy1" (the NumPy the reference documents); the product
     defaults to the regime of the installed NumPy.  Tests compare the two under one stated regime: numpy1 unless a
-    test selects the other itself (the reference-run fixtures, the numpy2 tests)."""
+    test selects the other itself with monkeypatch (the reference-run fixtures, the numpy2 tests).  Session scope:
+    module-scoped fixtures build their plans before any function-scoped fixture runs."""
     from xcontour_b200 import utils
-    monkeypatch.setattr(utils, "NUMPY_SCALAR_RULES", "numpy1")
+    old = utils.NUMPY_SCALAR_RULES
+    utils.NUMPY_SCALAR_RULES = "numpy1"
+    yield
+    utils.NUMPY_SCALAR_RULES = old
 
 
 @pytest.fixture(scope="session")

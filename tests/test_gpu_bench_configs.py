@@ -445,7 +445,7 @@ def test_interp_to_coords_pairs_slices_by_dimension_name(ops, vort):
 
 # ---------------------------------------------------------------- NumPy regime of the per-'time' edges, fused path
 @pytest.mark.parametrize("increase,lt", [(True, True), (False, False), (True, False)])
-def test_fused_batch_in_both_numpy_regimes(ops, increase, lt):
+def test_fused_batch_in_both_numpy_regimes(ops, monkeypatch, increase, lt):
     """core.py:1273-1281 builds the per-'time' edges with NumPy scalars: fp64 edges under NumPy 1.x, fp32 under
     NEP 50.  xc_keff_lwa_batch (ABI 3: numpy2_rules) reproduces either; each is held to the oracle's statement of
     the same regime, and the Contour2D hist path agrees with the fused path in both."""
@@ -469,7 +469,7 @@ def test_fused_batch_in_both_numpy_regimes(ops, increase, lt):
         assert relmax(out["intgrdS"].cpu().numpy(), ref_g) <= 1e-11
         areas[rules] = out["area"].cpu().numpy()
         # the drop-in API in the same regime
-        xutils.NUMPY_SCALAR_RULES = rules                           # (restored by the autouse fixture's monkeypatch)
+        monkeypatch.setattr(xutils, "NUMPY_SCALAR_RULES", rules)
         coords = {"time": np.arange(3), "latitude": lat, "longitude": lon}
         tr = xb.DataArray(q, dims=("time", "latitude", "longitude"), coords=coords, name="q")
         an = xb.Contour2D(tr, xb.DataArray(dA, dims=("latitude", "longitude")), dims={"X": "longitude", "Y": "latitude"},

@@ -792,6 +792,19 @@ def test_equal_area_levels_weighted_quantile_histogram(ops, vort, increase, lt):
         fr = fr if increase else 1 - fr          # decreasing levels enclose the complementary fraction
         exact = O.weighted_quantile_levels(q3[s], dA, fr)
         assert np.abs(lev.values[s][1:-1] - exact[1:-1]).max() <= 2 * step
+    # a single slice takes the static-bins branch of _histogram (edges in the contour dtype); straight through the C ABI
+    one = ops.equal_area_levels(dev(ops, q3[:1].reshape(1, -1)), dev(ops, dA.reshape(-1)), N, refine, increase, lt,
+                                0, False).cpu().numpy().astype(np.float32)
+    ref1 = O.cal_contours_equal_area(q3[:1], dA, N, increase, lt, np.float32, refine)
+    assert np.abs(one.view(np.int32) - ref1.view(np.int32)).max() <= 1
+    # fp64 levels, NumPy >= 2 edge rules
+    two = ops.equal_area_levels(dev(ops, q3.reshape(2, -1)), dev(ops, dA.reshape(-1)), N, refine, increase, lt,
+                                1, True).cpu().numpy()
+    fine = O.cal_contours(q3, (N - 1) * refine + 1, increase, np.float64)
+    area = O.cal_integral_within_contours_hist(q3, fine, dA, lt, scalar_rules="numpy2")
+    tgt = area[:, :1] + (area[:, -1:] - area[:, :1]) * np.linspace(0.0, 1.0, N)[None, :]
+    ref2 = np.stack([O.interp1d(tgt[s], area[s], fine[s], bool(area[0, 0] < area[0, -1])) for s in range(2)])
+    assert np.allclose(two, ref2, rtol=1e-12, atol=0)
 
 
 def test_device_cell_area(ops):

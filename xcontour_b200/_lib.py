@@ -56,6 +56,10 @@ SIGNATURES = {
     "xc_minmax_levels": (c_int, [c_void_p, c_int, c_long, c_long, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "xc_hist_edges": (c_int, [c_void_p, c_long, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "xc_equal_area_levels_workspace_bytes": (c_size_t, [c_long, c_long, c_int, c_int]),
+    "xc_equal_area_levels": (c_int, [c_void_p, c_int, c_long, c_long, c_void_p, c_int,
+                                     c_int, c_int, c_int, c_int, c_int, c_int,
+                                     c_void_p, c_void_p, c_size_t, c_void_p]),
     "xc_bin_accumulate_workspace_bytes": (c_size_t, [c_long, c_long, c_int, c_int]),
     "xc_bin_accumulate": (c_int, [c_void_p, c_int, c_long, c_long,
                                   c_void_p, c_long, c_int, c_int,

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libxcb200.so")
-SOURCES = ["api.cu", "levels.cu", "hist.cu", "bin_rows.cu", "contour_ops.cu", "lwa.cu", "lwa_fx.cu", "lwa_cols.cu", "grad2.cu", "epilogue.cu", "fused.cu"]
+SOURCES = ["api.cu", "levels.cu", "hist.cu", "bin_rows.cu", "contour_ops.cu", "lwa.cu", "lwa_fx.cu", "lwa_cols.cu", "grad2.cu", "epilogue.cu", "equal_area.cu", "fused.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
               "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

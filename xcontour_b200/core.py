@@ -215,22 +215,19 @@ class Contour2D(object):
         weights (cal_integral_within_contours_hist), the resulting A(q) relation
         is inverted by linear interpolation at ``levels`` equally spaced areas.
         Adjacent returned levels therefore enclose (to within one fine bin) the
-        same area increment.  Everything runs in the same kernels as the methods
-        it composes.
+        same area increment.  One library call (xc_equal_area_levels) chains the
+        kernels of the methods it composes on the device; only the levels come back.
         """
         N = int(levels)
-        fine = self.cal_contours((N - 1) * int(refine) + 1)
-        area = self.cal_integral_within_contours_hist(fine)
-        a, lead, lshape = self._flat2(area)
-        f, _, _ = self._flat2(fine)
-        at, ft = ops.to_dev(a.astype(np.float64)), ops.to_dev(f.astype(np.float64))
-        # N equally spaced target areas between the first and the last CDF value
-        w = torch.linspace(0.0, 1.0, N, dtype=torch.float64, device=at.device)
-        tgt = at[:, :1] + (at[:, -1:] - at[:, :1]) * w[None, :]
-        increasing = bool(a[0, 0] < a[0, -1])
-        out = ops.interp(tgt.contiguous(), at, ft, reverse=0 if increasing else 1)
-        res = out.cpu().numpy().astype(self.dtype).reshape(tuple(lshape) + (N,))
-        coords = xc.coords_for(fine, lead)
+        q, lead, plane = self._tracer_dev(None)
+        S = q.shape[0]
+        dA_dev, _ = self._dA_plane(plane, self.tracer)
+        # one call on the device (xc_equal_area_levels): levels -> edges -> area CDF -> inverse interpolation
+        out = ops.equal_area_levels(q.reshape(S, -1), dA_dev.reshape(-1), N, int(refine), self.increase, self.lt,
+                                    _np_dtype_code(self.dtype), utils.scalar_rules() == "numpy2")
+        lshape = tuple(self.tracer.shape[self.tracer.dims.index(d)] for d in lead)
+        res = out.cpu().numpy().astype(self.dtype).reshape(lshape + (N,))
+        coords = xc.coords_for(self.tracer, lead)
         coords['contour'] = np.linspace(0.0, N - 1.0, N, dtype=self.dtype)
         return xc.make(res, lead + ['contour'], coords, self.tracer.name)
 

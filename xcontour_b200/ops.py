@@ -97,6 +97,19 @@ def minmax_levels(q, N, increase, out_dtype=XC_F32):
     return levels, mm
 
 
+def equal_area_levels(q, dA, N, refine, increase, lt, out_dtype, numpy2_rules):
+    """q: [S, P] device tensor (fp32 / fp64), dA: [P] -> [S, N] fp64 levels rounded to out_dtype (xc_equal_area_levels)."""
+    lib = require_cuda()
+    S, P = q.shape
+    out = torch.empty((S, int(N)), dtype=torch.float64, device=q.device)
+    nb = lib.xc_equal_area_levels_workspace_bytes(S, P, int(N), int(refine))
+    ws = workspace(nb)
+    check(lib.xc_equal_area_levels(_p(q), fdtype(q), S, P, _p(dA), fdtype(dA), int(N), int(refine),
+                                   int(bool(increase)), int(bool(lt)), int(out_dtype), int(bool(numpy2_rules)),
+                                   _p(out), _p(ws), nb, stream_ptr()))
+    return out
+
+
 def hist_edges(levels, ctr_dtype, time_branch):
     lib = require_cuda()
     S, N = levels.shape
