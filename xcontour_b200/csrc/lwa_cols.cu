@@ -93,6 +93,7 @@ k_lwa_cols(const QT* __restrict__ q, long s0, int nslices, int ny, int nx,
     constexpr int LC_B = 4;                                      // cells per batch (LC_U is a multiple)
     constexpr int LC_NT = SEG * LC_TC;
     constexpr int LC_U = ((NYCAP + SEG - 1) / SEG + LC_B - 1) / LC_B * LC_B;      // rows a thread owns, at most
+    static_assert(FX_LUT % LC_NT == 0, "the LUT is copied in whole rounds of the CTA");
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr LwaColsSmem L = lwa_cols_layout(NYCAP, (int)sizeof(TT));
     long long* nxs = reinterpret_cast<long long*>(smem + L.nxs);
@@ -130,6 +131,11 @@ k_lwa_cols(const QT* __restrict__ q, long s0, int nslices, int ny, int nx,
         const FxScale* fp = fxs + sl;
         const double* Qg = Qref + s * (long)ny;
         // ---- phase 0: zero the planes, tables of a new slice, LUT ----
+        // (the LUT words come from L2 and are only needed at the end of the phase: requested first, so that their
+        // latency is spent behind the barrier and the zeroing instead of in front of the copy loop)
+        uint32_t pk[FX_LUT / LC_NT];
+#pragma unroll
+        for (int t = 0; t < FX_LUT / LC_NT; ++t) pk[t] = __ldg(lutg + (size_t)sl * FX_LUT + tid + t * LC_NT);
         __syncthreads();                                          // previous tile's walk is done with the planes / totals
         {
             uint4* zS = reinterpret_cast<uint4*>(smem + L.farS);          // the planes are NYCAP + 1 slots apart: zero the
@@ -154,10 +160,11 @@ k_lwa_cols(const QT* __restrict__ q, long s0, int nslices, int ny, int nx,
             scalef = fx_scale(qmin, qmax);
         }
         // LUT: first row of every bucket (+ the end marker), unpacked from the (first[b], first[b+1]) pairs
-        for (int k = tid; k < FX_LUT; k += LC_NT) {
-            const uint32_t pk = __ldg(lutg + (size_t)sl * FX_LUT + k);
-            lut[k] = (uint16_t)(pk & 0xffffu);
-            if (k == FX_LUT - 1) lut[FX_LUT] = (uint16_t)(pk >> 16);
+#pragma unroll
+        for (int t = 0; t < FX_LUT / LC_NT; ++t) {
+            const int k = tid + t * LC_NT;
+            lut[k] = (uint16_t)(pk[t] & 0xffffu);
+            if (k == FX_LUT - 1) lut[FX_LUT] = (uint16_t)(pk[t] >> 16);
         }
         __syncthreads();
 
