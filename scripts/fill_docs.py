@@ -32,7 +32,11 @@ if c5:
     sub["@C5_MS@"] = "%.3f" % (rc["stage_ms_per_step"]["bin_accumulate"] / n5)
     sub["@C5_EPI_MS@"] = "%.3f" % (rc["stage_ms_per_step"]["epilogue"] / n5)
     sub["@C5_FRAC@"] = "%.1f" % (100 * rc["frac"]); sub["@C5_VAL@"] = "%.0f" % c5["value"]
-sub["@V1@"] = "%.0f" % d["value"]; sub["@MS1@"] = "%.3f" % d["ms_per_step"]; sub["@E1@"] = "%.0f" % d["e2e"]["value"]
+# the N >= 2 lines are compared with the N = 1 line of the SAME library build (the multi-GPU runs were made before the
+# last kernel change of the round; profiles/<tag>_bench_n1_scaling_base.json is the N = 1 line of that build)
+base = line("bench_n1_scaling_base") or d
+sub["@V1@"] = "%.0f" % base["value"]; sub["@MS1@"] = "%.3f" % base["ms_per_step"]; sub["@E1@"] = "%.0f" % base["e2e"]["value"]
+d_final, d = d, base
 for n in (2, 4, 8):
     dn = line("bench_n%d" % n)
     if dn:
