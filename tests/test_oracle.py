@@ -371,3 +371,49 @@ def test_default_scalar_rules_follow_the_installed_numpy():
     assert utils.scalar_rules("numpy2") == "numpy2" and utils.scalar_rules() == "numpy1"      # conftest pins numpy1
     with pytest.raises(Exception, match="scalar rules"):
         utils.scalar_rules("numpy3")
+
+
+def test_contour_gather_packed_gloo_world2(tmp_path):
+    """The collective of the N > 1 path itself (pipeline.ContourGather: one packed [9, S_local, N] buffer per rank,
+    rotating receive buffers) on two gloo ranks: layout [world, 9, S_local, N], unpack() by name with the padded
+    tail trimmed, a second batch landing in the other receive buffer while the first stays intact."""
+    script = tmp_path / "g.py"
+    script.write_text(
+        "import sys, torch, torch.distributed as dist\n"
+        "sys.path.insert(0, %r)\n"
+        "from xcontour_b200.pipeline import ContourGather, CONTOUR_VARS, slice_range\n"
+        "dist.init_process_group('gloo')\n"
+        "r, w, S, N = dist.get_rank(), dist.get_world_size(), 7, 5\n"
+        "per = (S + w - 1) // w\n"
+        "lo, hi = slice_range(S, r, w)\n"
+        "def full(b):\n"
+        "    return torch.arange(9 * S * N, dtype=torch.float64).reshape(9, S, N) + 1000.0 * b\n"
+        "g = ContourGather(per, N, 'cpu', nbuf=2)\n"
+        "keep = []\n"
+        "for b in range(3):\n"
+        "    packed = torch.zeros((9, per, N), dtype=torch.float64)\n"
+        "    packed[:, :hi - lo] = full(b)[:, lo:hi]\n"
+        "    recv, idx = g.launch(packed)\n"
+        "    assert idx == b %% 2 and tuple(recv.shape) == (w, 9, per, N)\n"
+        "    out = ContourGather.unpack(recv, S)\n"
+        "    assert list(out) == list(CONTOUR_VARS)\n"
+        "    for i, name in enumerate(CONTOUR_VARS):\n"
+        "        assert torch.equal(out[name], full(b)[i]), (b, name)\n"
+        "    keep.append((recv, b))\n"
+        "    if b == 1:\n"
+        "        assert torch.equal(ContourGather.unpack(keep[0][0], S)['area'], full(0)[1])\n"
+        "g.wait()\n"
+        "try:\n"
+        "    g.launch(torch.zeros((9, per + 1, N), dtype=torch.float64)); raise SystemExit('no error')\n"
+        "except Exception as e:\n"
+        "    assert 'packed buffer' in str(e)\n"
+        "dist.barrier(); print('OK', r)\n" % ROOT)
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert res.stdout.count("OK") == 2

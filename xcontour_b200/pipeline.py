@@ -255,8 +255,9 @@ class HostStreamer(object):
 class ContourGather(object):
     """Asynchronous all-gather of the packed contour-space results ([9, S_local, N] per rank, see
     KeffLwaPlan.alloc_outputs) on a side stream: the collective of batch b overlaps the kernels of batch b+1.
-    The only communication of the whole path (SURVEY.md §8e); LWA fields stay sharded.  NCCL only (CUDA tensors);
-    every rank contributes the same S_local (the last batch of a run is padded by the caller).
+    The only communication of the whole path (SURVEY.md §8e); LWA fields stay sharded.  NCCL with CUDA tensors;
+    with CPU tensors (gloo: the host-logic tests) the same buffers and layout, the collective issued in place.
+    Every rank contributes the same S_local (the last batch of a run is padded by the caller).
     ``nbuf`` receive buffers rotate; ``wait()`` makes the current stream wait for every gather in flight."""
 
     def __init__(self, S_local, N, device, group=None, nbuf=2):
@@ -265,7 +266,8 @@ class ContourGather(object):
         self.world = dist.get_world_size(group)
         self.recv = [torch.empty((self.world, len(CONTOUR_VARS), S_local, N), dtype=torch.float64, device=device)
                      for _ in range(nbuf)]
-        self.stream = torch.cuda.Stream(device=device)
+        self.on_gpu = torch.device(device).type == "cuda"
+        self.stream = torch.cuda.Stream(device=device) if self.on_gpu else None
         self.done = [None] * nbuf
         self.n = 0
 
@@ -274,6 +276,11 @@ class ContourGather(object):
         [world, 9, S_local, N] it will land in, and the index to pass to ``event()``."""
         i = self.n % len(self.recv)
         self.n += 1
+        if tuple(packed.shape) != tuple(self.recv[i].shape[1:]):
+            raise Exception("ContourGather: packed buffer %s, expected %s" % (tuple(packed.shape), tuple(self.recv[i].shape[1:])))
+        if not self.on_gpu:
+            self.dist.all_gather_into_tensor(self.recv[i].view(-1), packed.contiguous().view(-1), group=self.group)
+            return self.recv[i], i
         ready = torch.cuda.Event()
         ready.record()
         with torch.cuda.stream(self.stream):
@@ -287,7 +294,8 @@ class ContourGather(object):
         return self.done[i]
 
     def wait(self):
-        torch.cuda.current_stream().wait_stream(self.stream)
+        if self.on_gpu:
+            torch.cuda.current_stream().wait_stream(self.stream)
 
     @staticmethod
     def unpack(recv, S_total=None):
