@@ -577,7 +577,7 @@ class Contour2D(object):
         def back(t, dtype=None):
             if not eq_first:
                 t = t.transpose(1, 2)
-            arr = t.cpu().numpy()
+            arr = ops.to_host(t)
             if dtype is not None:
                 arr = arr.astype(dtype)
             lead_shape = tuple(q.shape[q.dims.index(d)] for d in lead)

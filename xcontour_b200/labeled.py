@@ -64,7 +64,8 @@ class DataArray(object):
     @property
     def _data(self):
         if self._np is None:                       # device-backed: materialise on first host access
-            self._np = self._raw.detach().cpu().numpy()
+            from . import ops
+            self._np = ops.to_host(self._raw)
         return self._np
 
     @property

@@ -7,6 +7,7 @@ Nothing here falls back to the CPU: without a CUDA device, or without the
 built library, every function raises.
 """
 import ctypes
+import threading
 
 import numpy as np
 import torch
@@ -63,6 +64,56 @@ def to_dev(x, dtype=None):
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)
     return t.contiguous()
+
+
+_STAGE = {}
+_CHUNK = 8 << 20
+_NP_OF = {torch.float64: np.float64, torch.float32: np.float32, torch.int64: np.int64, torch.int32: np.int32,
+          torch.int16: np.int16, torch.int8: np.int8, torch.uint8: np.uint8, torch.bool: np.bool_}
+
+
+def _staging(dev_index):
+    """two pinned 8 MB buffers + their events per (host thread, device); idle on return"""
+    key = (threading.get_ident(), dev_index)
+    st = _STAGE.get(key)
+    if st is None:
+        st = _STAGE[key] = ([torch.empty(_CHUNK, dtype=torch.uint8, pin_memory=True) for _ in range(2)],
+                            [torch.cuda.Event() for _ in range(2)])
+    for e in st[1]:
+        e.synchronize()                                  # a DMA of an earlier transfer may still be reading them
+    return st
+
+
+def to_host(t):
+    """CUDA tensor -> a fresh NumPy array.  Large results (an LWA field is 8.3 MB per slice) go through two pinned
+    staging buffers: the DMA of chunk k+1 runs at the PCIe rate while chunk k is copied into the pageable result
+    (a plain ``.cpu()`` of a 66 MB field ran at 2.2 GB/s on the B200 boxes, 30 of the 42 ms of an 8-slice
+    Contour2D workflow).  The staging buffers are 2 x 8 MB per host thread and device; the result owns its memory."""
+    if not t.is_cuda:
+        return t.detach().numpy()
+    nbytes = t.numel() * t.element_size()
+    chunk_bytes = _CHUNK
+    if nbytes < 4 * chunk_bytes or t.dtype not in _NP_OF:
+        return t.detach().cpu().numpy()
+    t = t.detach().contiguous()
+    out = np.empty(tuple(t.shape), dtype=_NP_OF[t.dtype])
+    src = t.reshape(-1).view(torch.uint8)
+    dst = torch.from_numpy(out.reshape(-1).view(np.uint8))
+    n = (nbytes + chunk_bytes - 1) // chunk_bytes
+    with torch.cuda.device(t.device):
+        bufs, evs = _staging(t.device.index)
+        for k in range(n + 1):
+            if k < n:                                   # DMA of chunk k into the buffer chunk k-2 has left
+                lo = k * chunk_bytes
+                hi = min(nbytes, lo + chunk_bytes)
+                bufs[k & 1][:hi - lo].copy_(src[lo:hi], non_blocking=True)
+                evs[k & 1].record()
+            if k >= 1:                                  # chunk k-1 has landed: into the result
+                lo = (k - 1) * chunk_bytes
+                hi = min(nbytes, lo + chunk_bytes)
+                evs[(k - 1) & 1].synchronize()
+                dst[lo:hi].copy_(bufs[(k - 1) & 1][:hi - lo])
+    return out
 
 
 def fdtype(t):
