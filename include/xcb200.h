@@ -54,7 +54,8 @@ extern "C" {
 #define XC_BC_FILL     3 /* ghost = fill_value                       ['constant'] */
 
 const char* xc_last_error(void);
-int         xc_abi_version(void);
+#define XC_ABI_VERSION 3
+int         xc_abi_version(void);   /* == XC_ABI_VERSION of the header the library was built from */
 
 /* ------------------------------------------------------------------------
  * (1) contour levels -- Contour2D.cal_contours(levels:int), core.py:222-249.

@@ -34,6 +34,6 @@ int sm_count()
 }  // namespace xc
 
 extern "C" const char* xc_last_error(void) { return xc::g_err; }
-extern "C" int xc_abi_version(void) { return 3; }
+extern "C" int xc_abi_version(void) { return XC_ABI_VERSION; }
 extern "C" long xc_launch_count(void) { return xc::g_launches; }
 extern "C" void xc_reset_launch_count(void) { xc::g_launches = 0; }
