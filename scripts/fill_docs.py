@@ -21,7 +21,7 @@ sub = {"@VALUE@": "%.1f" % (d["value"] / 1e3), "@MS@": "%.3f" % d["ms_per_step"]
        "@MM_MS@": "%.3f" % st["minmax_levels"], "@MM_FRAC@": "%.0f" % (100 * fr["minmax_levels"]),
        "@EPI_MS@": "%.3f" % st["epilogue"],
        "@PIPE_FRAC@": "%.1f" % (100 * r["pipeline"]["frac"]), "@E2E@": "%.1f" % (d["e2e"]["value"] / 1e3),
-       "@C2D@": "%.0f" % d["e2e_contour2d"]["value"] if d.get("e2e_contour2d") else "n/a",
+       "@C2D@": "%.0f" % d["e2e_contour2d"]["value"] if (d.get("e2e_contour2d") or {}).get("value") else "n/a",
        "@CPU@": "%.2f" % d["cpu_baseline"]["value"], "@CORES@": "%d" % d["cpu_baseline"]["cores"]}
 if ref:
     sub["@REF@"] = "%.2f" % ref["value"]
