@@ -284,8 +284,8 @@ def run_ours_c5(args, rank, world, local_rank):
     from xcontour_b200._lib import N_STAGES, STAGE_NAMES
     from xcontour_b200.pipeline import KeffLwaPlan
     from xcontour_b200.utils import row_metrics_cartesian
+    ops.require_cuda()                       # no CUDA device or no built library: stop here, there is no CPU path
     torch.cuda.set_device(local_rank)
-    ops.require_cuda()
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
@@ -394,8 +394,8 @@ def run_ours(args, rank, world, local_rank):
     from xcontour_b200.pipeline import ContourGather, HostStreamer, KeffLwaPlan, bind_host_thread_to_gpu
     from xcontour_b200.utils import latlon_cell_area
 
+    ops.require_cuda()                       # no CUDA device or no built library: stop here, there is no CPU path
     torch.cuda.set_device(local_rank)
-    ops.require_cuda()
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=nccl_options())
     dev = torch.device("cuda", local_rank)

@@ -418,3 +418,25 @@ def test_contour_gather_packed_gloo_world2(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert res.returncode == 0, res.stdout + res.stderr
     assert res.stdout.count("OK") == 2
+
+
+def test_bench_contract_pieces_checkable_without_a_gpu():
+    """bench.py: the synthetic field is SURVEY 8(d)'s (and the one the parity tests use), both arms quote the same
+    metric / workload strings, the reference arm's line carries the keys the driver reads, and without a CUDA device
+    our arm fails loudly instead of measuring something else."""
+    import bench
+    lat, lon = bench.grid()
+    _, _, q = synth_c4(1)
+    assert np.array_equal(bench.synth_slice_np(0, lat, lon), q[0])
+    base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
+    assert (bench.NY, bench.NX, bench.NLEV) == (721, 1440, 361) and "721x1440" in bench.METRIC
+    assert "slices" in base["metric"].lower() and "721" in base["metric"]
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count('"workload": WORKLOAD') + src.count('"workload": C5_WORKLOAD if c5 else WORKLOAD') >= 2
+    for key in ('"impl": "reference"', '"cpu_baseline"', '"e2e"', '"roofline"', '"clocks"', '"gpu_launches"',
+                '"higher_is_better"', '"scaling"', '"vs_baseline"', '"ms_per_step"'):
+        assert key in src, key
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1", "--no-cpu"],
+                         cwd=ROOT, env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode != 0 and "no CPU fallback" in (res.stderr + res.stdout)
